@@ -1,0 +1,448 @@
+#!/usr/bin/env python
+"""Benchmark of the IC3Net rollout hot path on B200 (BASELINE.json metric:
+agent-env-steps/sec at 1/2/4/8 B200 vs the reference CPU path).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload pp_hard_ic3net] [--impl b200|reference]
+
+A "step" is one lock-step pass of the hot path over the whole env batch of a GPU:
+obs gather -> encoder -> comm/LSTM/heads/sampling -> env step (+ auto-reset), i.e.
+B*N agent-env-steps.  Prints ONE JSON line (see DESIGN.md "Measurement").
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "agent-env-steps/sec"
+
+WORKLOADS = {
+    # BASELINE.json configs[1]: predator_prey hard (10 agents, dim 20, vision 1, 80 steps) IC3Net, 8192 envs / GPU
+    "pp_hard_ic3net": dict(env_name="predator_prey", nagents=10, dim=20, vision=1, max_steps=80, nenvs=8192,
+                           ic3net=True, mode="mixed"),
+    # configs[3]
+    "pp_hard_commnet": dict(env_name="predator_prey", nagents=10, dim=20, vision=1, max_steps=80, nenvs=8192,
+                            ic3net=False, mode="mixed"),
+    # configs[2]: traffic_junction medium (README: vision 0, add_rate .05/.02)
+    "tj_medium_ic3net": dict(env_name="traffic_junction", nagents=10, dim=14, vision=0, max_steps=40, nenvs=8192,
+                             ic3net=True, difficulty="medium", add_rate_min=0.05, add_rate_max=0.02,
+                             curr_start=0, curr_end=0),
+    # configs[4]
+    "tj_hard_ic3net": dict(env_name="traffic_junction", nagents=20, dim=18, vision=0, max_steps=80, nenvs=4096,
+                           ic3net=True, difficulty="hard", add_rate_min=0.02, add_rate_max=0.05,
+                           curr_start=250, curr_end=1250),
+    # configs[0] (the reference's own CPU-runnable parity case)
+    "pp_easy_ic3net": dict(env_name="predator_prey", nagents=3, dim=5, vision=0, max_steps=20, nenvs=8192,
+                           ic3net=True, mode="mixed"),
+}
+
+
+def make_args(wl, rank=0, obs_mode="dense", nenvs=None):
+    d = dict(hid_size=128, recurrent=True, rnn_type="LSTM", commnet=True, hard_attn=False, comm_action_one=False,
+             comm_mode="avg", comm_passes=1, comm_mask_zero=False, comm_init="uniform", share_weights=False,
+             continuous=False, batch_size=500, lrate=1e-3, nenemies=1, no_stay=False, moving_prey=False,
+             enemy_comm=False, mode="mixed", vocab_type="bool", add_rate_min=0.05, add_rate_max=0.2, curr_start=0,
+             curr_end=0, difficulty="easy", seed=1, mean_ratio=1.0, obs_mode=obs_mode, use_graph=False)
+    d.update(WORKLOADS[wl])
+    if nenvs:
+        d["nenvs"] = nenvs
+    a = argparse.Namespace(**d)
+    if a.ic3net:                       # main.py:115-123
+        a.hard_attn, a.mean_ratio = True, 0
+        if a.env_name == "traffic_junction":
+            a.comm_action_one = True
+    a.nfriendly = a.nagents
+    a.env_id0 = rank * a.nenvs
+    return a
+
+
+def heads_of(a):
+    na = 5 if a.env_name == "predator_prey" else 2
+    return [na, 2] if a.hard_attn else [na]
+
+
+# ------------------------------------------------------------------------------
+# CPU arm (oracle port of the reference, one env per process)
+# ------------------------------------------------------------------------------
+def cpu_cfg(wl):
+    a = make_args(wl)
+    args = {k: v for k, v in vars(a).items() if isinstance(v, (int, float, str, bool))}
+    cfg = dict(args=args, heads=heads_of(a))
+    if a.env_name == "traffic_junction":
+        cfg["tables"] = os.path.join(ROOT, "tests", "golden", "tj_tables_%s_%d.npz" % (a.difficulty, a.dim))
+    return cfg
+
+
+def run_cpu(wl, nprocs, budget_s, nsamples=1):
+    """Run in a fresh interpreter so no CUDA context is ever forked/shared."""
+    out = subprocess.check_output([sys.executable, "-m", "oracle.cpu_baseline", json.dumps(cpu_cfg(wl)),
+                                   str(nprocs), str(budget_s), str(nsamples)], cwd=ROOT)
+    return json.loads(out.decode().strip().split("\n")[-1])
+
+
+def reference_arm(opts):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    cores = os.cpu_count() or 1
+    K, W = opts.steps, opts.warmup
+    budget = max(0.5, min(15.0, 90.0 / max(1, K + W)))   # each "step" = one bounded sample; whole run ends in minutes
+    r = run_cpu(opts.workload, cores, budget, W + K)
+    vals = r["samples"][W:]
+    secs = sum(x[1] for x in vals)
+    v = sum(x[0] for x in vals) * WORKLOADS[opts.workload]["nagents"] / secs
+    a = make_args(opts.workload)
+    line = dict(metric=METRIC, value=v, unit="agent-env-steps/s", n_gpus=opts.gpus, steps=K, warmup=W,
+                ms_per_step=1e3 * secs / K, higher_is_better=True, scaling="weak",
+                vs_baseline=None, dtype="f64", data="synthetic", impl="reference",
+                config=dict(workload=opts.workload, envs_per_process=1, nagents=a.nagents, max_steps=a.max_steps),
+                cpu_baseline=dict(value=v, unit="agent-env-steps/s", cores=cores, kind="port",
+                                  sample="%d processes x %.1f s of oracle get_episode loops (1 env each, float64, "
+                                         "OMP_NUM_THREADS=1) per step" % (cores, budget)),
+                e2e=dict(value=v, unit="agent-env-steps/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0),
+                gpu_launches=0)
+    print(json.dumps(line))
+    return 0
+
+
+# ------------------------------------------------------------------------------
+# clocks
+# ------------------------------------------------------------------------------
+class ClockSampler(object):
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self._stop = index, [], threading.Event()
+        self.th = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.check_output(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                               "--format=csv,noheader,nounits"], timeout=5).decode().strip()
+                self.rows.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def __enter__(self):
+        self.th.start()
+        return self
+
+    def __exit__(self, *e):
+        self._stop.set()
+        self.th.join(timeout=6)
+
+    def summary(self):
+        sm = sorted(int(float(r[0])) for r in self.rows if r and r[0].replace(".", "").isdigit())
+        mx = [int(float(r[1])) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 3 + i and r[3 + i] == "Active" for r in self.rows)]
+        return dict(sm_mhz=sm[len(sm) // 2] if sm else None, sm_max_mhz=max(mx) if mx else None, reasons=reasons,
+                    samples=len(self.rows))
+
+
+# ------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------
+def gpu_arm(opts):
+    import ctypes as C
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    from ic3net_b200 import _lib, data
+    from ic3net_b200.action_utils import parse_action_args, select_action
+    from ic3net_b200.comm import CommNetMLP
+    from ic3net_b200.trainer import Trainer
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    K, W = opts.steps, max(3, opts.warmup)
+
+    def build(obs_mode, nenvs=None):
+        a = make_args(opts.workload, rank, obs_mode, nenvs)
+        env = data.init(a.env_name, a)
+        a.num_inputs = env.observation_dim
+        a.num_actions = [env.num_actions] + ([2] if a.hard_attn else [])
+        a.dim_actions = len(a.num_actions)
+        parse_action_args(a)
+        torch.manual_seed(0)            # random-init weights of the reference architecture, identical on every rank
+        net = CommNetMLP(a, a.num_inputs)
+        return a, env, net, Trainer(a, net, env)
+
+    a, env, net, tr = build(opts.obs_mode)
+    B, N, H, O = a.nenvs, a.nagents, a.hid_size, a.num_inputs
+    nparam = sum(p.numel() for n_, p in net.named_parameters() if not n_.startswith("hidd_encoder"))
+    grad_flat = torch.zeros(nparam + 64, device=dev)       # REINFORCE gradient + packed stat scalars
+
+    def timed_rollout(trn, steps, record_kernels=False):
+        """Enqueue `steps` lock-step iterations; returns device ms (and per-kernel ms when asked)."""
+        b = trn._buf
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        trn._enqueue(steps)
+        if world > 1:
+            dist.all_reduce(grad_flat)                       # one collective per update (multi_processing.py:90-95)
+        e1.record()
+        return e0, e1
+
+    # ---- warm-up + timed region (value: inputs resident in HBM, no host sync inside) ----
+    tr._alloc(max(K, W))
+    env.env.reset(want_obs=False) if a.env_name == "predator_prey" else env.env.reset(0, want_obs=False)
+    tr._enqueue(W)
+    if world > 1:
+        dist.all_reduce(grad_flat)
+    torch.cuda.synchronize()
+    launches0 = _lib.launch_count()
+    with ClockSampler(local) as clk:
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = timed_rollout(tr, K)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        ms = e0.elapsed_time(e1)
+        time.sleep(0.25)
+    launches = _lib.launch_count() - launches0
+    t = torch.tensor([ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    tr.collect_stat()                                         # raises on any device-side error flag
+    value = world * B * N * K / (ms * 1e-3)
+
+    line = None
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+        peak_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
+
+        # ---- per-kernel device times (separate pass, CUDA events around every launch) ----
+        kern = per_kernel_times(tr, a, env, net, min(K, 20), C, torch, _lib)
+        is_pp = a.env_name == "predator_prey"
+        state_bytes = 32 if is_pp else 64
+        obs_bytes = (4 * O + state_bytes) * B * N             # obs written once + state/action/reward
+        roof = None
+        if "obs_gather" in kern:
+            ach = obs_bytes / (kern["obs_gather"] * 1e-3) / 1e9
+            roof = dict(kernel="obs_gather", bound="hbm", achieved=ach, peak=hbm_peak, unit="GB/s",
+                        frac=ach / hbm_peak, traffic=None, peak_source=peak_src,
+                        algorithmic_bytes_per_launch=obs_bytes, avg_launch_ms=kern["obs_gather"])
+        kinfo = {}
+        for k, v in kern.items():
+            kinfo[k] = dict(avg_ms=v)
+        if "encoder_dense" in kern:
+            eb = (4 * O + 4 * H) * B * N
+            kinfo["encoder_dense"].update(bytes=eb, gbs=eb / (kern["encoder_dense"] * 1e-3) / 1e9,
+                                          hbm_frac=eb / (kern["encoder_dense"] * 1e-3) / 1e9 / hbm_peak)
+        if "policy_step" in kern:
+            fl = (2 * H * H + 16 * H * H) * B * N
+            pb = (20 * H + 4 * (sum(a.naction_heads) + 1) + 8) * B * N
+            kinfo["policy_step"].update(flops=fl, tflops=fl / (kern["policy_step"] * 1e-3) / 1e12, bytes=pb,
+                                        gbs=pb / (kern["policy_step"] * 1e-3) / 1e9, math="fp32 SIMT (policy v1)")
+
+        # ---- fused index-form rollout (no [B,N,O] tensor) as a second data point ----
+        alt = None
+        if opts.obs_mode == "dense" and world == 1:
+            a2, env2, net2, tr2 = build("index")
+            tr2._alloc(max(K, W))
+            env2.env.reset(want_obs=False) if is_pp else env2.env.reset(0, want_obs=False)
+            tr2._enqueue(W)
+            torch.cuda.synchronize()
+            f0, f1 = timed_rollout(tr2, K)
+            torch.cuda.synchronize()
+            ms2 = f0.elapsed_time(f1)
+            alt = dict(obs_mode="index", value=B * N * K / (ms2 * 1e-3), ms_per_step=ms2 / K,
+                       note="same rollout with the encoder evaluated from the env state (bit-identical x)")
+            del tr2, net2, env2
+
+        # ---- e2e: the public, reference-shaped API with host-side actions / rewards ----
+        e2e = e2e_loop(a, env, net, min(K, 20), np, torch, select_action)
+
+        # ---- CPU baseline (bounded sample of the same workload on the host cores) ----
+        cores = os.cpu_count() or 1
+        cpu = run_cpu(opts.workload, cores, 12.0) if world == 1 else None
+
+        line = dict(metric=METRIC, value=value, unit="agent-env-steps/s", n_gpus=world, steps=K, warmup=W,
+                    ms_per_step=ms / K, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32",
+                    data="synthetic",
+                    config=dict(workload=opts.workload, envs_per_gpu=B, nagents=N, obs_dim=O, hid_size=H,
+                                max_steps=a.max_steps, obs_mode=opts.obs_mode, parallelism="dp%d" % world,
+                                l2="per-step working set %.2f GB > 126 MB L2 (inputs larger than L2)"
+                                   % ((8 * O + 20 * H) * B * N / 1e9),
+                                weights="random init (torch.manual_seed(0)), reference architecture"),
+                    clocks=clk.summary(), gpu_launches=launches, e2e=e2e, roofline=roof, kernels=kinfo)
+        if alt:
+            line["fused_index_rollout"] = alt
+        if cpu:
+            line["cpu_baseline"] = dict(value=cpu["value"], unit="agent-env-steps/s", cores=cores, kind="port",
+                                        sample="%d processes x 12 s of oracle get_episode loops (1 env each, "
+                                               "float64, OMP_NUM_THREADS=1)" % cores)
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def per_kernel_times(tr, a, env, net, steps, C, torch, _lib):
+    """Average device time of each kernel of the step, CUDA events around every launch."""
+    lib = _lib.load()
+    e, b = env.env, tr._buf
+    B = e.nenvs
+    cfg = net.policy_cfg(B)
+    cfg.seed, cfg.env_id0 = e.cfg.seed, e.cfg.env_id0
+    w = net.packed()
+    s = _lib.stream()
+    is_tj = a.env_name == "traffic_junction"
+    hard = int(bool(a.hard_attn))
+    nh = len(a.naction_heads)
+    ev = {}
+
+    def timed(name, fn):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        _lib.check(fn())
+        e1.record()
+        ev.setdefault(name, []).append((e0, e1))
+
+    for t in range(steps):
+        if tr.obs_mode == "dense":
+            if is_tj:
+                timed("obs_gather", lambda: lib.ic3_tj_obs(C.byref(e.cfg), C.byref(e.state), b["obs"].data_ptr(), s))
+            else:
+                timed("obs_gather", lambda: lib.ic3_pp_obs(C.byref(e.cfg), C.byref(e.state), b["obs"].data_ptr(), s))
+            timed("encoder_dense", lambda: lib.ic3_encoder_dense(C.byref(cfg), C.byref(w), b["obs"].data_ptr(),
+                                                                 b["x"].data_ptr(), s))
+        elif is_tj:
+            timed("encoder_index", lambda: lib.ic3_tj_encoder_index(C.byref(e.cfg), C.byref(e.state), C.byref(cfg),
+                                                                    C.byref(w), b["x"].data_ptr(), s))
+        else:
+            timed("encoder_index", lambda: lib.ic3_pp_encoder_index(C.byref(e.cfg), C.byref(e.state), C.byref(cfg),
+                                                                    C.byref(w), b["x"].data_ptr(), s))
+        io = _lib.PolicyIO(x=b["x"].data_ptr(), h=b["h"].data_ptr(), c=b["c"].data_ptr(),
+                           comm_action=b["comm"].data_ptr() if hard else None, alive=b["alive"].data_ptr(),
+                           fresh=b["fresh"].data_ptr(), tick=e.tick.data_ptr(), draws=None, h_out=b["h"].data_ptr(),
+                           c_out=b["c"].data_ptr(), value=b["value"][t].data_ptr(), logp=b["logp"][t].data_ptr(),
+                           action=b["action"][t].data_ptr())
+        timed("policy_step", lambda: lib.ic3_policy_step(C.byref(cfg), C.byref(w), C.byref(io), s))
+        r = _lib.RolloutIO(t=t, max_steps=a.max_steps, nheads=nh, hard_attn=hard,
+                           comm_action_one=int(bool(a.comm_action_one)), last=0, action=b["action"][t].data_ptr(),
+                           t_ep=b["t_ep"].data_ptr(), fresh=b["fresh"].data_ptr(), comm_next=b["comm"].data_ptr(),
+                           alive_next=b["alive"].data_ptr(), rec_reward=b["reward"].data_ptr(),
+                           rec_episode_mask=b["emask"].data_ptr(), rec_mini_mask=b["mini"].data_ptr(),
+                           rec_alive=b["ralive"].data_ptr(), stat_reward=b["stat_reward"].data_ptr(),
+                           stat_comm=b["stat_comm"].data_ptr(), stat_success=b["stat_success"].data_ptr(),
+                           stat_episodes=b["stat_episodes"].data_ptr(), stat_steps=b["stat_steps"].data_ptr())
+        if is_tj:
+            timed("env_step", lambda: lib.ic3_tj_step(C.byref(e.cfg), C.byref(e.state), b["action"][t].data_ptr(), nh,
+                                                      None, b["step_reward"].data_ptr(), None, b["err"].data_ptr(),
+                                                      C.byref(r), s))
+        else:
+            timed("env_step", lambda: lib.ic3_pp_step(C.byref(e.cfg), C.byref(e.state), b["action"][t].data_ptr(), nh,
+                                                      b["step_reward"].data_ptr(), None, b["err"].data_ptr(),
+                                                      C.byref(r), s))
+    torch.cuda.synchronize()
+    return {k: sum(x.elapsed_time(y) for x, y in v) / len(v) for k, v in ev.items()}
+
+
+def e2e_loop(a, env, net, steps, np, torch, select_action):
+    """The reference-shaped call sequence of Trainer.get_episode (trainer.py:43-108) with HOST arrays for
+    everything the reference keeps in numpy (actions, comm_action, alive_mask, reward, done); observations
+    and hidden states stay in HBM.  Pinned host buffers; every step synchronises like the reference does."""
+    B, N = a.nenvs, a.nagents
+    nh = len(a.naction_heads)
+    is_tj = a.env_name == "traffic_junction"
+    e = env.env
+    e.strict = False
+    pin = lambda *s, dtype: torch.empty(*s, dtype=dtype).pin_memory()
+    act_h, rew_h, done_h = pin(B, N, nh, dtype=torch.int32), pin(B, N, dtype=torch.float32), pin(B, dtype=torch.bool)
+    alive_h = pin(B, N, dtype=torch.uint8)
+    comm_h = pin(B, N, dtype=torch.uint8)
+    env_act_h = pin(B, N, dtype=torch.int32)
+    h2d = d2h = 0
+
+    def one_step(obs, hc, info, count):
+        nonlocal h2d, d2h
+        action_out, value, hc = net([obs, hc], info)                     # comm_action / alive_mask: host -> device
+        action = select_action(a, action_out)
+        act_h.copy_(action, non_blocking=True)                           # D2H (translate_action -> numpy)
+        torch.cuda.synchronize()
+        env_act_h.copy_(act_h[..., 0])
+        obs, reward, done, info_env = env.step([env_act_h])              # H2D actions
+        rew_h.copy_(reward, non_blocking=True)                           # D2H
+        done_h.copy_(done, non_blocking=True)
+        nxt = {}
+        if a.hard_attn:
+            comm_h.copy_(act_h[..., -1] if not a.comm_action_one else torch.ones(B, N, dtype=torch.uint8))
+            nxt["comm_action"] = comm_h
+        if is_tj:
+            alive_h.copy_(info_env["alive_mask"], non_blocking=True)     # D2H
+            nxt["alive_mask"] = alive_h
+        torch.cuda.synchronize()
+        if count:
+            h2d += env_act_h.numel() * 4 + (comm_h.numel() if a.hard_attn else 0) + (alive_h.numel() if is_tj else 0)
+            d2h += act_h.numel() * 4 + rew_h.numel() * 4 + done_h.numel() + (alive_h.numel() if is_tj else 0)
+        if not is_tj and bool(done_h.any()):                             # finished PP envs start a new episode
+            m = done_h.to(torch.uint8)
+            e.reset(mask=m, want_obs=False)
+            obs = env._flatten_obs(e._get_obs())
+            keep = (~done_h).to(obs.device).repeat_interleave(N).unsqueeze(1).float()
+            hc = (hc[0] * keep, hc[1] * keep)
+            if a.hard_attn:
+                comm_h.mul_((~done_h).to(torch.uint8).unsqueeze(1))
+        return obs, hc, nxt
+
+    obs = env.reset(0)
+    hc = net.init_hidden(B)
+    info = {"comm_action": torch.zeros(B, N, dtype=torch.uint8).pin_memory()} if a.hard_attn else {}
+    for _ in range(3):
+        obs, hc, info = one_step(obs, hc, info, False)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        obs, hc, info = one_step(obs, hc, info, True)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    e.err.zero_()
+    return dict(value=B * N * steps / dt, unit="agent-env-steps/s", h2d_bytes_per_step=h2d // steps,
+                d2h_bytes_per_step=d2h // steps, steps=steps, ms_per_step=1e3 * dt / steps,
+                api="CommNetMLP.forward -> select_action -> host actions -> GymWrapper.step -> host reward/done")
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=80)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="pp_hard_ic3net", choices=sorted(WORKLOADS))
+    ap.add_argument("--obs_mode", default="dense", choices=["dense", "index"])
+    opts = ap.parse_args()
+    if opts.impl == "reference":
+        return reference_arm(opts)
+    return gpu_arm(opts)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,75 @@
+"""Counterpart of the reference ``action_utils.py`` (:5-63) for batched CUDA tensors.
+
+``select_action`` replaces ``torch.multinomial`` (action_utils.py:35) by inverse-CDF
+sampling in a CUDA kernel, driven by the library's Philox action stream or by
+explicit 24-bit draws; ``translate_action`` keeps the reference's return shape
+``(action, actual)`` = per-head lists, now of ``[B, N]`` int32 CUDA tensors.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+
+
+def parse_action_args(args):
+    # action_utils.py:5-25
+    if args.num_actions[0] > 0:
+        args.continuous = False
+        args.naction_heads = [int(args.num_actions[i]) for i in range(args.dim_actions)]
+    else:
+        actions_heads = args.nactions.split(':')
+        if len(actions_heads) == 1 and int(actions_heads[0]) == 1:
+            args.continuous = True
+        elif len(actions_heads) == 1 and int(actions_heads[0]) > 1:
+            args.continuous = False
+            args.naction_heads = [int(actions_heads[0]) for _ in range(args.dim_actions)]
+        elif len(actions_heads) > 1:
+            args.continuous = False
+            args.naction_heads = [int(i) for i in actions_heads]
+        else:
+            raise RuntimeError("--nactions wrong format!")
+
+
+_ticks = {}
+
+
+def select_action(args, action_out, draws=None, tick=None):
+    """action_out: list over heads of log-probs [B, N, na].  Returns int32 [B, N, heads].
+
+    draws: optional explicit 24-bit uniforms [B, N, heads]; otherwise the Philox action
+    stream (seed = args.seed) at ``tick`` ([B] int32 tensor; by default an internal
+    per-args call counter)."""
+    if args.continuous:
+        raise NotImplementedError("continuous actions are outside the accelerated path")
+    logp = torch.cat([a.to(torch.float32) for a in action_out], dim=-1).contiguous()
+    B, N = logp.shape[0], logp.shape[1]
+    heads = [int(a.shape[-1]) for a in action_out]
+    hd = (C.c_int32 * _lib.MAX_HEADS)(*(heads + [0] * (_lib.MAX_HEADS - len(heads))))
+    cfg = _lib.PolicyCfg(B=B, N=N, H=32, O=1, nheads=len(heads), head_dim=hd, hard_attn=0, comm_avg=0,
+                         comm_mask_zero=0, env_id0=int(getattr(args, 'env_id0', 0)),
+                         seed=int(getattr(args, 'seed', 0)) & 0xFFFFFFFFFFFFFFFF)
+    d = None
+    if draws is not None:
+        d = torch.as_tensor(np.asarray(draws.cpu() if torch.is_tensor(draws) else draws, dtype=np.int64))
+        d = d.to(logp.device, torch.int32).reshape(B, N, len(heads)).contiguous()
+    elif tick is None:
+        key = id(args)
+        if key not in _ticks or _ticks[key].shape[0] != B:
+            _ticks[key] = torch.zeros(B, dtype=torch.int32, device=logp.device)
+        tick = _ticks[key].clone()
+        _ticks[key] += 1
+    action = torch.empty(B, N, len(heads), dtype=torch.int32, device=logp.device)
+    _lib.check(_lib.load().ic3_sample_actions(C.byref(cfg), logp.data_ptr(), _lib.ptr(tick), _lib.ptr(d),
+                                              action.data_ptr(), _lib.stream()))
+    return action
+
+
+def translate_action(args, env, action):
+    # action_utils.py:39-43 (discrete branch): per-head arrays; `actual` is what the env gets
+    if args.num_actions[0] > 0:
+        action = [action[..., k].contiguous() for k in range(action.shape[-1])]
+        actual = action
+        return action, actual
+    raise NotImplementedError("continuous / scaled actions are outside the accelerated path")

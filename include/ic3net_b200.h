@@ -1,0 +1,254 @@
+/*
+ * ic3net_b200 -- C ABI of the B200-native IC3Net rollout hot path.
+ *
+ * The reference (IC3Net/IC3Net) is pure Python and has no FFI layer; its boundary
+ * for this path is the duck-typed Python surface listed below.  Every entry
+ * point here names the reference interface (file:line under /root/reference) it
+ * replaces; the Python classes in ic3net_b200/ keep that surface and call these
+ * functions through ctypes (see INTEGRATION.md for the binding a maintainer adds).
+ *
+ * Conventions
+ *   - plain C types only; every pointer inside the *_state / *_io / *_weights
+ *     structs is a DEVICE pointer owned by the caller (PyTorch is only the
+ *     container); the structs themselves live in host memory;
+ *   - every call enqueues work on the caller's `stream` (a cudaStream_t passed
+ *     as void*) and returns immediately: 0 = ok, <0 = IC3_E_* argument error,
+ *     >0 = cudaError_t of the launch;
+ *   - misuse that the reference reports with a Python exception *during* a step
+ *     ("Episode is done", predator_prey_env.py:129-130, traffic_junction_env.py:
+ *     222-223; route overrun :570-572) is recorded in a caller-supplied device
+ *     flag word `err` (bit IC3_ERR_*), which the Python layer turns into the same
+ *     exception at its next host read;
+ *   - one host thread per GPU, no re-entrancy (the reference is single-threaded,
+ *     multi_processing.py:7).
+ *
+ * Randomness: counter-based Philox4x32-10, key = seed, counter =
+ * (env_id0 + env, tick, stream, index); see ic3net_b200/csrc/ic3_rng.cuh.  Every
+ * stochastic entry point also accepts explicit 24-bit draws ("tape") instead.
+ */
+#ifndef IC3NET_B200_H
+#define IC3NET_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define IC3_MAX_AGENTS 32   /* one warp lane per agent */
+#define IC3_MAX_HEADS 4
+#define IC3_MAX_HEAD_DIM 16
+
+enum {
+  IC3_OK = 0,
+  IC3_E_NULL = -1,        /* required pointer missing */
+  IC3_E_RANGE = -2,       /* size / enum out of the supported range */
+  IC3_E_UNSUPPORTED = -3  /* configuration the kernels do not implement */
+};
+
+enum {
+  IC3_ERR_EPISODE_DONE = 1, /* step() on a finished episode */
+  IC3_ERR_ROUTE_OVERRUN = 2,
+  IC3_ERR_BAD_ACTION = 4    /* action > naction (reference asserts, :137 / :228) */
+};
+
+enum { IC3_PP_MIXED = 0, IC3_PP_COOPERATIVE = 1, IC3_PP_COMPETITIVE = 2 };
+
+const char* ic3_version(void);
+const char* ic3_strerror(int code);
+/* number of kernels launched by this library since load (bench.py "gpu_launches") */
+uint64_t ic3_launch_count(void);
+
+/* ------------------------------------------------------------------------
+ * Predator-prey  (ic3net_envs/predator_prey_env.py)
+ * ---------------------------------------------------------------------- */
+typedef struct {
+  int32_t B;        /* environments in the batch */
+  int32_t N;        /* predators (args.nfriendly, :79) ; one fixed prey (:78) */
+  int32_t dim;      /* board is dim x dim (:80) */
+  int32_t vision;   /* window is (2v+1)^2 (:107) */
+  int32_t mode;     /* IC3_PP_* (:262-269) */
+  int32_t naction;  /* 5, or 4 with --no_stay (:88-92) */
+  uint32_t env_id0; /* global id of env 0 (rank * B): RNG stream selector */
+  uint64_t seed;
+} ic3_pp_cfg;
+
+typedef struct {
+  int32_t* loc;      /* [B, N+1, 2] (row, col); predators then prey (:158-159) */
+  uint8_t* reached;  /* [B, N] reached_prey (:155,271) */
+  uint8_t* done;     /* [B] episode_over (:154,273-274) */
+  int32_t* success;  /* [B] stat['success'] (:284-288), -1 when unset */
+  uint32_t* episode; /* [B] resets so far (tick of the spawn stream) */
+  uint32_t* tick;    /* [B] env steps so far (tick of the action stream) */
+} ic3_pp_state;
+
+/* Trainer-side bookkeeping fused into the env step kernels when `r` is non-NULL:
+ * the per-step tail of Trainer.get_episode (trainer.py:69-108) plus auto-reset,
+ * so a batch of B independent env slots can run T lock-step iterations with no
+ * host round trip.  All pointers are device pointers; rec_* may be NULL. */
+typedef struct {
+  int32_t t;               /* lock-step index into the rec_* arrays */
+  int32_t max_steps;       /* args.max_steps (trainer.py:43,90) */
+  int32_t nheads;          /* columns of `action` */
+  int32_t hard_attn;       /* args.hard_attn && args.commnet (trainer.py:70) */
+  int32_t comm_action_one; /* args.comm_action_one (trainer.py:71) */
+  int32_t last;            /* 1 on the final lock-step of the batch: open episodes are cut (treated like max_steps) */
+  const int32_t* action;   /* [B, N, nheads] sampled this step; env consumes head 0 (env_wrappers.py:76-77) */
+  int32_t* t_ep;           /* [B] step index inside the current episode */
+  uint8_t* fresh;          /* [B] out: next policy step starts an episode (h=c=0, nobody talks, all alive; trainer.py:45-51) */
+  uint8_t* comm_next;      /* [B, N] out: info['comm_action'] for the next policy step (trainer.py:70-71) */
+  uint8_t* alive_next;     /* [B, N] out: info['alive_mask'] for the next policy step (comm.py:102-104) */
+  float* rec_reward;       /* [T, B, N] */
+  uint8_t* rec_episode_mask; /* [T, B]  0 on the last step of an episode (trainer.py:92-96) */
+  uint8_t* rec_mini_mask;  /* [T, B, N] 1 - is_completed on non-final steps (trainer.py:97-99) */
+  uint8_t* rec_alive;      /* [T, B, N] misc['alive_mask'] (trainer.py:78-81) */
+  float* stat_reward;      /* [B, N] += reward          (trainer.py:86) */
+  float* stat_comm;        /* [B, N] += comm_next       (trainer.py:73) */
+  int32_t* stat_success;   /* [B] += env.stat['success'] at episode end (trainer.py:124-125) */
+  int32_t* stat_episodes;  /* [B] += 1 at episode end   (trainer.py:235) */
+  int32_t* stat_steps;     /* [B] += 1 every step       (trainer.py:109) */
+} ic3_rollout_io;
+
+/* reset(): predator_prey_env.py:146-168.  Draws N+1 distinct cells per env from
+ * the spawn stream (law of np.random.choice(dim*dim, N+1, replace=False), :174).
+ * mask: [B] uint8 or NULL (= all).  obs: [B,N,O] float or NULL. */
+int ic3_pp_reset(const ic3_pp_cfg* cfg, const ic3_pp_state* st, const uint8_t* mask,
+                 float* obs, void* stream);
+/* step(action): predator_prey_env.py:112-144 (+ _take_action :212-252, _get_reward
+ * :254-290, _get_obs :188-210 when obs != NULL).  act: [B,N] int32 (stride
+ * act_stride ints per agent, so a [B,N,heads] action tensor can be passed directly).
+ * reward: [B,N] float.  err: device flag word. */
+int ic3_pp_step(const ic3_pp_cfg* cfg, const ic3_pp_state* st, const int32_t* act, int32_t act_stride,
+                float* reward, float* obs, int32_t* err, const ic3_rollout_io* r, void* stream);
+/* _get_obs + env_wrappers._flatten_obs: predator_prey_env.py:188-210, env_wrappers.py:88-100.
+ * obs: [B, N, W*W*V] float32, window-major then class. */
+int ic3_pp_obs(const ic3_pp_cfg* cfg, const ic3_pp_state* st, float* obs, void* stream);
+
+/* ------------------------------------------------------------------------
+ * Traffic junction  (ic3net_envs/traffic_junction_env.py, traffic_helper.py)
+ * ---------------------------------------------------------------------- */
+typedef struct {
+  int32_t B, N, vision;
+  int32_t h, w;            /* dims (already +1 for easy, :112-115) */
+  int32_t G, P, Lmax;      /* arrival groups, paths per group, longest path */
+  int32_t outside_cls;     /* OUTSIDE_CLASS = BASE (:129) */
+  int32_t car_cls;         /* CAR_CLASS = BASE + 2 (:130) */
+  int32_t vocab;           /* vocab_size = BASE + 3 (:132) */
+  int32_t npath;           /* nPr(nroad, 2) (:126) */
+  uint32_t spawn_thr;      /* floor(add_rate * 2^24): u <= add_rate (:375) on 24-bit draws */
+  uint32_t env_id0;
+  uint64_t seed;
+  const int32_t* grid;        /* [h, w] road ids / OUTSIDE (:300-316) */
+  const int32_t* route_len;   /* [G, P] */
+  const int32_t* route_cells; /* [G, P, Lmax] (row << 16 | col) (traffic_helper.py:156-209) */
+} ic3_tj_cfg;
+
+typedef struct {
+  int32_t* loc;        /* [B, N, 2] car_loc; dead cars sit at (0,0) (:185,565) */
+  uint8_t* alive;      /* [B, N] alive_mask */
+  int32_t* wait;       /* [B, N] */
+  int32_t* route_id;   /* [B, N] p + g*P, -1 before the first spawn (:177,385) */
+  int32_t* route_pos;  /* [B, N] car_route_loc (:188) */
+  uint8_t* last_act;   /* [B, N] car_last_act (:186), survives respawn */
+  uint8_t* completed;  /* [B, N] is_completed of the last step (:233) */
+  int32_t* cars_in_sys;/* [B] */
+  uint8_t* has_failed; /* [B] sticky per episode (:171,592) */
+  uint32_t* tick;      /* [B] env steps so far */
+} ic3_tj_state;
+
+/* reset(epoch): traffic_junction_env.py:160-204 (the curriculum, :196-200,620-626,
+ * is host arithmetic that only changes cfg->spawn_thr). */
+int ic3_tj_reset(const ic3_tj_cfg* cfg, const ic3_tj_state* st, const uint8_t* mask,
+                 float* obs, void* stream);
+/* step(action): traffic_junction_env.py:206-252 (_take_action :540-581, _add_cars
+ * :369-393, _choose_dead :614-618, _get_reward :585-595).  draws: [B,G,3] 24-bit
+ * ints (spawn test, dead slot, path) or NULL for the Philox spawn stream. */
+int ic3_tj_step(const ic3_tj_cfg* cfg, const ic3_tj_state* st, const int32_t* act, int32_t act_stride,
+                const uint32_t* draws, float* reward, float* obs, int32_t* err,
+                const ic3_rollout_io* r, void* stream);
+/* _get_obs + _flatten_obs: traffic_junction_env.py:321-366, env_wrappers.py:88-100.
+ * obs: [B, N, 2 + W*W*V] float32. */
+int ic3_tj_obs(const ic3_tj_cfg* cfg, const ic3_tj_state* st, float* obs, void* stream);
+
+/* ------------------------------------------------------------------------
+ * CommNet / IC3Net policy step  (comm.py:134-244, action_utils.py:27-36)
+ * ---------------------------------------------------------------------- */
+typedef struct {
+  int32_t B, N, H, O;      /* envs, agents, hid_size (32|64|128), obs dim */
+  int32_t nheads;          /* len(args.naction_heads) */
+  int32_t head_dim[IC3_MAX_HEADS];
+  int32_t hard_attn;       /* args.hard_attn (comm.py:171) */
+  int32_t comm_avg;        /* args.comm_mode == 'avg' (comm.py:194) */
+  int32_t comm_mask_zero;  /* args.comm_mask_zero (comm.py:39-43) */
+  uint32_t env_id0;
+  uint64_t seed;
+} ic3_policy_cfg;
+
+/* Parameters in the reference state_dict layout (device, fp32). */
+typedef struct {
+  const float* encoder_w;  /* [H, O] */
+  const float* encoder_b;  /* [H] */
+  const float* c_w;        /* C_modules.0.weight [H, H] */
+  const float* c_b;        /* [H] */
+  const float* w_ih;       /* f_module.weight_ih [4H, H] gate order i,f,g,o */
+  const float* w_hh;       /* f_module.weight_hh [4H, H] */
+  const float* b_ih;       /* [4H] */
+  const float* b_hh;       /* [4H] */
+  const float* value_w;    /* value_head.weight [1, H] */
+  const float* value_b;    /* [1] */
+  const float* head_w[IC3_MAX_HEADS]; /* heads.k.weight [na_k, H] */
+  const float* head_b[IC3_MAX_HEADS]; /* [na_k] */
+} ic3_policy_params;
+
+/* Kernel-side layout, produced once per weight update by ic3_policy_pack. */
+typedef struct {
+  float* enc_wT;   /* [O, H]       encoder.weight^T: one contiguous H-row per obs feature */
+  float* enc_b;    /* [H] */
+  float* c_wT;     /* [H, H]       c_wT[k][n] = C.weight[n][k] */
+  float* c_b;      /* [H] */
+  float* lstm_wT;  /* [2H, 4H]     rows 0..H-1 <- w_ih^T, rows H..2H-1 <- w_hh^T; column 4*u+gate */
+  float* lstm_b;   /* [4H]         b_ih + b_hh, column 4*u+gate */
+  float* head_w;   /* [1+sum(na), H]  row 0 = value head, then heads in order */
+  float* head_b;   /* [1+sum(na)] */
+} ic3_policy_packed;
+
+int ic3_policy_pack(const ic3_policy_cfg* cfg, const ic3_policy_params* p,
+                    const ic3_policy_packed* out, void* stream);
+
+/* x = encoder(obs): comm.py:119.  Exact for any dense obs; cost scales with the
+ * number of non-zeros per row (one-hot observations: ~1% dense). */
+int ic3_encoder_dense(const ic3_policy_cfg* cfg, const ic3_policy_packed* w, const float* obs,
+                      float* x, void* stream);
+/* Same x computed straight from the env state (no [B,N,O] tensor is materialised). */
+int ic3_pp_encoder_index(const ic3_pp_cfg* env, const ic3_pp_state* st, const ic3_policy_cfg* cfg,
+                         const ic3_policy_packed* w, float* x, void* stream);
+int ic3_tj_encoder_index(const ic3_tj_cfg* env, const ic3_tj_state* st, const ic3_policy_cfg* cfg,
+                         const ic3_policy_packed* w, float* x, void* stream);
+
+typedef struct {
+  const float* x;             /* [B*N, H] encoder output */
+  const float* h;             /* [B*N, H] prev hidden  (comm.py:122) */
+  const float* c;             /* [B*N, H] prev cell */
+  const uint8_t* comm_action; /* [B, N] info['comm_action'] (required when hard_attn) */
+  const uint8_t* alive;       /* [B, N] info['alive_mask'] or NULL = all alive (comm.py:102-107) */
+  const uint8_t* fresh;       /* [B] or NULL; 1 = episode start: h=c=0, comm_action=0, alive=1 (trainer.py:45-51) */
+  const uint32_t* tick;       /* [B] action-stream tick per env, or NULL = 0 */
+  const uint32_t* draws;      /* [B, N, nheads] 24-bit draws, or NULL = Philox action stream */
+  float* h_out;               /* [B*N, H] */
+  float* c_out;               /* [B*N, H] */
+  float* value;               /* [B*N]    value_head (comm.py:228) */
+  float* logp;                /* [B, N, sum(na)] log_softmax per head, heads concatenated (comm.py:239) */
+  int32_t* action;            /* [B, N, nheads] sampled actions or NULL (action_utils.py:32-36) */
+} ic3_policy_io;
+
+/* One CommNetMLP.forward (recurrent branch, comm_passes = 1) + select_action. */
+int ic3_policy_step(const ic3_policy_cfg* cfg, const ic3_policy_packed* w, const ic3_policy_io* io,
+                    void* stream);
+/* select_action alone (action_utils.py:32-36) on given log-probabilities. */
+int ic3_sample_actions(const ic3_policy_cfg* cfg, const float* logp, const uint32_t* tick,
+                       const uint32_t* draws, int32_t* action, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* IC3NET_B200_H */

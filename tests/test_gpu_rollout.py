@@ -1,0 +1,170 @@
+"""GPU parity tests of the fused lock-step rollout (ic3net_b200/trainer.py) against
+(a) whole episodes recorded from the unmodified reference's Trainer.get_episode
+(tests/golden/ep_*.npz) and (b) the oracle replaying every env slot with the same
+Philox streams.  Integer outputs (actions, masks, alive) must be identical, rewards
+equal float32(reference), float outputs within 1e-5 * max(1,|ref|)."""
+import numpy as np
+import pytest
+import torch
+
+from helpers import finish_args, golden_names, load_golden, make_oracle_env, ns, tj_tables
+from oracle import policy as opolicy
+from oracle.gen_golden import make_weights
+from oracle.rollout import run_episode
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-5
+
+
+def close(a, b, tol=TOL):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    return np.all(np.abs(a - b) <= tol * np.maximum(1.0, np.abs(b)))
+
+
+def cpu(t):
+    return t.detach().cpu().numpy()
+
+
+def build(meta, B, obs_mode="index", use_graph=False, seed=None, env_id0=0, **over):
+    from ic3net_b200 import data
+    from ic3net_b200.comm import CommNetMLP
+    from ic3net_b200.trainer import Trainer
+    args = ns(meta["args"], nenvs=B, seed=meta["seed"] if seed is None else seed, env_id0=env_id0,
+              obs_mode=obs_mode, use_graph=use_graph, **over)
+    env = data.init(args.env_name, args)
+    finish_args(args, env)
+    net = CommNetMLP(args, args.num_inputs)
+    sd = make_weights(meta["weights_seed"], args.num_inputs, args.hid_size, args.naction_heads, args.comm_init)
+    net.load_state_dict({k: torch.from_numpy(v).float() for k, v in sd.items()})
+    return args, env, net, Trainer(args, net, env), opolicy.params_to_f64(sd)
+
+
+@pytest.mark.parametrize("name", golden_names("ep_"))
+@pytest.mark.parametrize("obs_mode", ["index", "dense"])
+def test_first_episode_matches_reference_golden(name, obs_mode):
+    meta, z = load_golden(name)
+    ids = meta["env_ids"]
+    B = max(ids) + 1
+    args, env, net, tr, p = build(meta, B, obs_mode)
+    T = args.max_steps
+    batch = tr.rollout(T, meta["epoch"])
+    torch.cuda.synchronize()
+    for i, env_id in enumerate(ids):
+        g = lambda k: z["e%d_%s" % (i, k)]
+        L = len(g("act"))
+        act = cpu(batch.action)[:L, env_id]
+        flips = (act != g("act")) & (g("margin") > 1e-4)
+        assert not flips.any(), (name, env_id)
+        if not np.array_equal(act, g("act")):
+            continue        # an fp32-borderline draw flipped; the teacher-forced test below covers this slot
+        assert np.array_equal(cpu(batch.reward)[:L, env_id], g("reward").astype(np.float32))
+        assert np.array_equal(cpu(batch.alive_mask)[:L, env_id], g("alive"))
+        assert np.array_equal(cpu(batch.episode_mask)[:L, env_id], g("emask")[:, 0])
+        assert np.array_equal(cpu(batch.episode_mini_mask)[:L, env_id], g("mini"))
+        assert close(cpu(batch.value)[:L, env_id], g("value")), (name, env_id)
+        lp = np.concatenate([g("logp%d" % k) for k in range(len(meta["heads"]))], -1)
+        assert close(cpu(batch.logp)[:L, env_id], lp), (name, env_id)
+
+
+@pytest.mark.parametrize("name,B,T", [("ep_pp_easy_ic3net", 11, 70), ("ep_tj_medium_ic3net", 7, 80),
+                                      ("ep_tj_easy_ic3net", 9, 45), ("ep_pp_hard_commnet", 3, 90),
+                                      ("ep_tj_medium_v1_commnet", 4, 50)])
+def test_lockstep_rollout_matches_oracle(name, B, T):
+    """Every slot, every episode (auto-reset, cut at the batch end), teacher-forced with
+    the GPU's own actions so both sides stay on one trajectory; plus the stat sums."""
+    meta, z = load_golden(name)
+    args, env, net, tr, p = build(meta, B, "index", seed=321, env_id0=50)
+    is_tj = args.env_name == "traffic_junction"
+    batch = tr.rollout(T, 0)
+    stat = tr.collect_stat()
+    act, rew = cpu(batch.action), cpu(batch.reward)
+    val, lp = cpu(batch.value), cpu(batch.logp)
+    emask, mini, alive = cpu(batch.episode_mask), cpu(batch.episode_mini_mask), cpu(batch.alive_mask)
+    tot = dict(reward=np.zeros(args.nagents), comm=np.zeros(args.nagents), success=0, episodes=0, flips=0, draws=0)
+    for b in range(B):
+        t0, k = 0, 0
+        orc = make_oracle_env(args, tj_tables(z) if is_tj else None)
+        while t0 < T:
+            ep = run_episode(orc, p, args, 321, 50 + b, epoch=0, tick0=t0, episode=k,
+                             forced_actions=act[t0:, b], max_steps=min(args.max_steps, T - t0))
+            L = ep["num_steps"]
+            sl = slice(t0, t0 + L)
+            assert np.array_equal(rew[sl, b], ep["reward"].astype(np.float32)), (b, k)
+            assert np.array_equal(emask[sl, b], ep["emask"][:, 0]) and np.array_equal(mini[sl, b], ep["mini"])
+            assert np.array_equal(alive[sl, b], ep["alive"])
+            assert close(val[sl, b], ep["value"]) and close(lp[sl, b], ep["logp"]), (b, k)
+            # free-running agreement of the sampled actions wherever fp32 cannot flip the draw
+            own = np.array([opolicy.sample_actions(np.split(ep["logp"][t], np.cumsum(args.naction_heads)[:-1], -1),
+                                                   opolicy.action_draws(321, 50 + b, t0 + t, args.nagents,
+                                                                        len(args.naction_heads)))[0]
+                            for t in range(L)])
+            safe = ep["margin"] > 1e-4
+            assert np.array_equal(own[safe], act[sl, b][safe])
+            tot["flips"] += int((own != act[sl, b]).sum())
+            tot["draws"] += own.size
+            tot["reward"] += ep["reward"].sum(0)
+            if args.hard_attn:
+                tot["comm"] += ep["comm_in"][1:].sum(0) + (act[t0 + L - 1, b, :, -1] if not args.comm_action_one
+                                                           else np.ones(args.nagents))
+            tot["success"] += max(ep["success"], 0)
+            tot["episodes"] += 1
+            t0 += L
+            k += 1
+    assert tot["flips"] <= 1e-3 * tot["draws"]
+    assert stat["num_steps"] == B * T and stat["num_episodes"] == tot["episodes"]
+    assert np.allclose(stat["reward"], tot["reward"], rtol=1e-5, atol=1e-4)
+    assert stat["success"] == tot["success"]
+    if args.hard_attn:
+        assert np.array_equal(stat["comm_action"], tot["comm"])
+
+
+def test_graph_replay_equals_eager():
+    """The graph trainer's first call = warm-up pass + captured pass, its second call = one
+    replay; so its second call must equal an eager trainer's third rollout bit for bit."""
+    meta, z = load_golden("ep_tj_medium_ic3net")
+    args, env, net, tr, p = build(meta, 16, "index", use_graph=True, seed=5)
+    tr.rollout(40, 0)
+    bg = tr.rollout(40, 0)
+    torch.cuda.synchronize()
+    g = (cpu(bg.action).copy(), cpu(bg.reward).copy(), cpu(bg.value).copy())
+    args, env, net, tr, p = build(meta, 16, "index", use_graph=False, seed=5)
+    tr.rollout(40, 0)
+    tr.rollout(40, 0)
+    b3 = tr.rollout(40, 0)
+    torch.cuda.synchronize()
+    assert np.array_equal(cpu(b3.action), g[0])
+    assert np.array_equal(cpu(b3.reward), g[1])
+    assert np.array_equal(cpu(b3.value), g[2])
+
+
+def test_dense_and_index_rollouts_are_identical():
+    meta, z = load_golden("ep_pp_hard_ic3net")
+    res = []
+    for mode in ("index", "dense"):
+        args, env, net, tr, p = build(meta, 24, mode, seed=77)
+        b = tr.rollout(30, 0)
+        torch.cuda.synchronize()
+        res.append((cpu(b.action).copy(), cpu(b.value).copy(), cpu(b.reward).copy()))
+    assert np.array_equal(res[0][0], res[1][0]) and np.array_equal(res[0][1], res[1][1])
+    assert np.array_equal(res[0][2], res[1][2])
+
+
+def test_pp_hard_full_size_rollout_properties():
+    """BASELINE c2 at full size (8192 envs): invariants of a 20-step lock-step rollout."""
+    meta, z = load_golden("ep_pp_hard_ic3net")
+    B, T = 8192, 20
+    args, env, net, tr, p = build(meta, B, "index", seed=9)
+    b = tr.rollout(T, 0)
+    stat = tr.collect_stat()
+    assert stat["num_steps"] == B * T
+    r = b.reward
+    assert bool(((r == 0) | (r == -0.05)).all())                        # mixed mode rewards
+    lp = b.logp.double().exp()
+    assert torch.allclose(lp[..., :5].sum(-1), torch.ones_like(lp[..., 0]), atol=1e-5)
+    assert torch.allclose(lp[..., 5:].sum(-1), torch.ones_like(lp[..., 0]), atol=1e-5)
+    assert int(b.action[..., 0].min()) >= 0 and int(b.action[..., 0].max()) <= 4
+    assert int(b.action[..., 1].min()) >= 0 and int(b.action[..., 1].max()) <= 1
+    assert bool((b.episode_mask[:-1] == 1).all() | (stat["num_episodes"] > B))
+    assert bool((b.episode_mask[-1] == 0).all())                         # batch end cuts every open episode
+    assert abs(stat["reward"].sum() - float(r.double().sum())) < 1e-2 * B
+    assert torch.isfinite(b.value).all()
