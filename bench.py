@@ -86,11 +86,23 @@ def run_cpu(wl, nprocs, budget_s, nsamples=1):
     return json.loads(out.decode().strip().split("\n")[-1])
 
 
+def host_cores():
+    """Host threads this process may actually use: affinity mask capped by the cgroup CPU quota."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        quota, period = open("/sys/fs/cgroup/cpu.max").read().split()
+        if quota != "max":
+            n = min(n, max(1, int(float(quota) / float(period))))
+    except Exception:
+        pass
+    return max(1, n)
+
+
 def reference_arm(opts):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    cores = os.cpu_count() or 1
+    cores = host_cores()
     K, W = opts.steps, opts.warmup
     budget = max(0.5, min(15.0, 90.0 / max(1, K + W)))   # each "step" = one bounded sample; whole run ends in minutes
     r = run_cpu(opts.workload, cores, budget, W + K)
@@ -120,34 +132,49 @@ class ClockSampler(object):
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
-        self.index, self.rows, self._stop = index, [], threading.Event()
+        self.index, self.rows, self.proc = index, [], None
         self.th = threading.Thread(target=self._run, daemon=True)
 
     def _run(self):
-        while not self._stop.is_set():
-            try:
-                out = subprocess.check_output(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                               "--format=csv,noheader,nounits"], timeout=5).decode().strip()
-                self.rows.append([x.strip() for x in out.split(",")])
-            except Exception:
-                pass
-            self._stop.wait(0.2)
+        try:
+            for ln in self.proc.stdout:
+                self.rows.append([x.strip() for x in ln.decode().strip().split(",")] + [time.time()])
+        except Exception:
+            pass
 
     def __enter__(self):
-        self.th.start()
+        try:    # one streaming nvidia-smi (a sample every 50 ms) for the duration of the timed region
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL)
+            self.th.start()
+            time.sleep(0.3)
+        except Exception:
+            self.proc = None
         return self
 
     def __exit__(self, *e):
-        self._stop.set()
-        self.th.join(timeout=6)
+        if self.proc is not None:
+            self.proc.terminate()          # exact PID we started
+            try:
+                self.proc.wait(timeout=5)
+            except Exception:
+                self.proc.kill()
+            self.th.join(timeout=5)
 
-    def summary(self):
-        sm = sorted(int(float(r[0])) for r in self.rows if r and r[0].replace(".", "").isdigit())
-        mx = [int(float(r[1])) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+    def summary(self, window=None):
+        """Median SM clock and throttle reasons over the samples that arrived inside `window`
+        (wall-clock start/end of the timed region; a sample lags the GPU state by <= 50 ms)."""
+        rows = self.rows
+        if window is not None:
+            inside = [r for r in rows if window[0] <= r[-1] <= window[1] + 0.06]
+            rows = inside or rows
+        sm = sorted(int(float(r[0])) for r in rows if r and str(r[0]).replace(".", "").isdigit())
+        mx = [int(float(r[1])) for r in rows if len(r) > 1 and str(r[1]).replace(".", "").isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any(len(r) > 3 + i and r[3 + i] == "Active" for r in self.rows)]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 3 + i and r[3 + i] == "Active" for r in rows)]
         return dict(sm_mhz=sm[len(sm) // 2] if sm else None, sm_max_mhz=max(mx) if mx else None, reasons=reasons,
-                    samples=len(self.rows))
+                    samples=len(rows))
 
 
 # ------------------------------------------------------------------------------
@@ -190,21 +217,29 @@ def gpu_arm(opts):
     nparam = sum(p.numel() for n_, p in net.named_parameters() if not n_.startswith("hidd_encoder"))
     grad_flat = torch.zeros(nparam + 64, device=dev)       # REINFORCE gradient + packed stat scalars
 
-    def timed_rollout(trn, steps, record_kernels=False):
-        """Enqueue `steps` lock-step iterations; returns device ms (and per-kernel ms when asked)."""
-        b = trn._buf
+    chunk = a.max_steps                                      # record buffers hold one episode horizon
+
+    def enqueue(trn, steps):
+        done = 0
+        while done < steps:                                  # episode-horizon chunks reuse the record buffers
+            n = min(chunk, steps - done)
+            trn._enqueue(n)
+            done += n
+
+    def timed_rollout(trn, steps):
+        """Enqueue `steps` lock-step iterations (+ the per-update gradient all-reduce); device events."""
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        trn._enqueue(steps)
+        enqueue(trn, steps)
         if world > 1:
             dist.all_reduce(grad_flat)                       # one collective per update (multi_processing.py:90-95)
         e1.record()
         return e0, e1
 
     # ---- warm-up + timed region (value: inputs resident in HBM, no host sync inside) ----
-    tr._alloc(max(K, W))
+    tr._alloc(chunk)
     env.env.reset(want_obs=False) if a.env_name == "predator_prey" else env.env.reset(0, want_obs=False)
-    tr._enqueue(W)
+    enqueue(tr, W)
     if world > 1:
         dist.all_reduce(grad_flat)
     torch.cuda.synchronize()
@@ -213,12 +248,14 @@ def gpu_arm(opts):
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+        wall0 = time.time()
         e0, e1 = timed_rollout(tr, K)
         torch.cuda.synchronize()
+        wall1 = time.time()
         if world > 1:
             dist.barrier()
         ms = e0.elapsed_time(e1)
-        time.sleep(0.25)
+        time.sleep(0.2)
     launches = _lib.launch_count() - launches0
     t = torch.tensor([ms], device=dev, dtype=torch.float64)
     if world > 1:
@@ -263,11 +300,11 @@ def gpu_arm(opts):
 
         # ---- fused index-form rollout (no [B,N,O] tensor) as a second data point ----
         alt = None
-        if opts.obs_mode == "dense" and world == 1:
+        if opts.obs_mode == "dense" and world == 1 and not opts.quick:
             a2, env2, net2, tr2 = build("index")
-            tr2._alloc(max(K, W))
+            tr2._alloc(chunk)
             env2.env.reset(want_obs=False) if is_pp else env2.env.reset(0, want_obs=False)
-            tr2._enqueue(W)
+            enqueue(tr2, W)
             torch.cuda.synchronize()
             f0, f1 = timed_rollout(tr2, K)
             torch.cuda.synchronize()
@@ -277,11 +314,11 @@ def gpu_arm(opts):
             del tr2, net2, env2
 
         # ---- e2e: the public, reference-shaped API with host-side actions / rewards ----
-        e2e = e2e_loop(a, env, net, min(K, 20), np, torch, select_action)
+        e2e = None if opts.quick else e2e_loop(a, env, net, min(K, 40), np, torch, select_action)
 
         # ---- CPU baseline (bounded sample of the same workload on the host cores) ----
-        cores = os.cpu_count() or 1
-        cpu = run_cpu(opts.workload, cores, 12.0) if world == 1 else None
+        cores = host_cores()
+        cpu = run_cpu(opts.workload, cores, 12.0) if (world == 1 and not opts.quick) else None
 
         line = dict(metric=METRIC, value=value, unit="agent-env-steps/s", n_gpus=world, steps=K, warmup=W,
                     ms_per_step=ms / K, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32",
@@ -291,7 +328,7 @@ def gpu_arm(opts):
                                 l2="per-step working set %.2f GB > 126 MB L2 (inputs larger than L2)"
                                    % ((8 * O + 20 * H) * B * N / 1e9),
                                 weights="random init (torch.manual_seed(0)), reference architecture"),
-                    clocks=clk.summary(), gpu_launches=launches, e2e=e2e, roofline=roof, kernels=kinfo)
+                    clocks=clk.summary((wall0, wall1)), gpu_launches=launches, e2e=e2e, roofline=roof, kernels=kinfo)
         if alt:
             line["fused_index_rollout"] = alt
         if cpu:
@@ -433,11 +470,12 @@ def e2e_loop(a, env, net, steps, np, torch, select_action):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=80)
+    ap.add_argument("--steps", type=int, default=400)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="pp_hard_ic3net", choices=sorted(WORKLOADS))
     ap.add_argument("--obs_mode", default="dense", choices=["dense", "index"])
+    ap.add_argument("--quick", action="store_true", help="skip the e2e / index / CPU legs (profiling runs)")
     opts = ap.parse_args()
     if opts.impl == "reference":
         return reference_arm(opts)
