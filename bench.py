@@ -203,6 +203,7 @@ def gpu_arm(opts):
 
     def build(obs_mode, nenvs=None):
         a = make_args(opts.workload, rank, obs_mode, nenvs)
+        a.policy_impl = opts.policy_impl
         env = data.init(a.env_name, a)
         a.num_inputs = env.observation_dim
         a.num_actions = [env.num_actions] + ([2] if a.hard_attn else [])
@@ -296,7 +297,9 @@ def gpu_arm(opts):
             fl = (2 * H * H + 16 * H * H) * B * N
             pb = (20 * H + 4 * (sum(a.naction_heads) + 1) + 8) * B * N
             kinfo["policy_step"].update(flops=fl, tflops=fl / (kern["policy_step"] * 1e-3) / 1e12, bytes=pb,
-                                        gbs=pb / (kern["policy_step"] * 1e-3) / 1e9, math="fp32 SIMT (policy v1)")
+                                        gbs=pb / (kern["policy_step"] * 1e-3) / 1e9,
+                                        math="tcgen05 kind::f16 hi/lo split, fp32 accumulate (prep + lstm_tc + heads)"
+                                        if net.policy_impl == "tc" else "fp32 SIMT (policy v1)")
 
         # ---- fused index-form rollout (no [B,N,O] tensor) as a second data point ----
         alt = None
@@ -381,7 +384,8 @@ def per_kernel_times(tr, a, env, net, steps, C, torch, _lib):
                            comm_action=b["comm"].data_ptr() if hard else None, alive=b["alive"].data_ptr(),
                            fresh=b["fresh"].data_ptr(), tick=e.tick.data_ptr(), draws=None, h_out=b["h"].data_ptr(),
                            c_out=b["c"].data_ptr(), value=b["value"][t].data_ptr(), logp=b["logp"][t].data_ptr(),
-                           action=b["action"][t].data_ptr())
+                           action=b["action"][t].data_ptr(), workspace=_lib.ptr(net.workspace(B)[0]),
+                           err=b["err"].data_ptr())
         timed("policy_step", lambda: lib.ic3_policy_step(C.byref(cfg), C.byref(w), C.byref(io), s))
         r = _lib.RolloutIO(t=t, max_steps=a.max_steps, nheads=nh, hard_attn=hard,
                            comm_action_one=int(bool(a.comm_action_one)), last=0, action=b["action"][t].data_ptr(),
@@ -475,6 +479,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="pp_hard_ic3net", choices=sorted(WORKLOADS))
     ap.add_argument("--obs_mode", default="dense", choices=["dense", "index"])
+    ap.add_argument("--policy_impl", default=None, choices=["tc", "simt"],
+                    help="tcgen05 tensor-core policy kernels (default for hid_size 128) or the fp32 SIMT kernel")
     ap.add_argument("--quick", action="store_true", help="skip the e2e / index / CPU legs (profiling runs)")
     opts = ap.parse_args()
     if opts.impl == "reference":

@@ -15,6 +15,7 @@ LIB_PATH = os.path.join(_HERE, "libic3net_b200.so")
 MAX_AGENTS = 32
 MAX_HEADS = 4
 MAX_HEAD_DIM = 16
+LSTM_IMG_BYTES = 786432
 
 ERR_EPISODE_DONE = 1
 ERR_ROUTE_OVERRUN = 2
@@ -68,12 +69,13 @@ class PolicyParams(C.Structure):
 
 class PolicyPacked(C.Structure):
     _fields_ = [("enc_wT", _p), ("enc_b", _p), ("c_wT", _p), ("c_b", _p), ("lstm_wT", _p), ("lstm_b", _p),
-                ("head_w", _p), ("head_b", _p)]
+                ("head_w", _p), ("head_b", _p), ("lstm_img", _p), ("bias_cat", _p)]
 
 
 class PolicyIO(C.Structure):
     _fields_ = [("x", _p), ("h", _p), ("c", _p), ("comm_action", _p), ("alive", _p), ("fresh", _p), ("tick", _p),
-                ("draws", _p), ("h_out", _p), ("c_out", _p), ("value", _p), ("logp", _p), ("action", _p)]
+                ("draws", _p), ("h_out", _p), ("c_out", _p), ("value", _p), ("logp", _p), ("action", _p),
+                ("workspace", _p), ("err", _p)]
 
 
 # every symbol include/ic3net_b200.h declares: name -> (restype, argtypes)
@@ -96,6 +98,7 @@ SYMBOLS = {
                                        C.POINTER(PolicyPacked), _PTR, _PTR]),
     "ic3_tj_encoder_index": (C.c_int, [C.POINTER(TJCfg), C.POINTER(TJState), C.POINTER(PolicyCfg),
                                        C.POINTER(PolicyPacked), _PTR, _PTR]),
+    "ic3_policy_workspace_bytes": (C.c_uint64, [C.POINTER(PolicyCfg)]),
     "ic3_policy_step": (C.c_int, [C.POINTER(PolicyCfg), C.POINTER(PolicyPacked), C.POINTER(PolicyIO), _PTR]),
     "ic3_sample_actions": (C.c_int, [C.POINTER(PolicyCfg), _PTR, _PTR, _PTR, _PTR, _PTR]),
 }

@@ -70,10 +70,29 @@ class CommNetMLP(nn.Module):
                                seed=int(getattr(args, 'seed', 0)) & 0xFFFFFFFFFFFFFFFF)
         self._packed = None
         self._packed_key = None
+        # 'tc' = tcgen05 tensor-core path (csrc/policy_tc.cu, hid_size 128), 'simt' = fp32 CUDA-core kernel
+        self.policy_impl = getattr(args, 'policy_impl', None) or ('tc' if H == 128 else 'simt')
+        if self.policy_impl not in ('tc', 'simt'):
+            raise ValueError("policy_impl must be 'tc' or 'simt'")
+        if self.policy_impl == 'tc' and H != 128:
+            raise NotImplementedError("the tensor-core policy path is specialised for hid_size 128")
+        self._ws = {}
 
     # ---- kernel-side weights ---------------------------------------------------
     def policy_cfg(self, B):
         return _lib.PolicyCfg(B=B, **self._cfg_proto)
+
+    def workspace(self, B):
+        """(scratch, err) tensors of the tensor-core path for a batch of B envs (None, None for 'simt')."""
+        if self.policy_impl != 'tc':
+            return None, None
+        if B not in self._ws:
+            cfg = self.policy_cfg(B)
+            nbytes = int(_lib.load().ic3_policy_workspace_bytes(C.byref(cfg)))
+            dev = self.encoder.weight.device
+            self._ws[B] = (torch.empty(nbytes, dtype=torch.uint8, device=dev),
+                           torch.zeros(1, dtype=torch.int32, device=dev))
+        return self._ws[B]
 
     def _param_list(self):
         ps = [self.encoder.weight, self.encoder.bias, self.C_modules[0].weight, self.C_modules[0].bias,
@@ -97,6 +116,9 @@ class CommNetMLP(nn.Module):
                               c_wT=torch.empty(H, H, device=dev), c_b=torch.empty(H, device=dev),
                               lstm_wT=torch.empty(2 * H, 4 * H, device=dev), lstm_b=torch.empty(4 * H, device=dev),
                               head_w=torch.empty(nout, H, device=dev), head_b=torch.empty(nout, device=dev))
+            if self.policy_impl == 'tc':
+                self._bufs['lstm_img'] = torch.empty(_lib.LSTM_IMG_BYTES, dtype=torch.uint8, device=dev)
+                self._bufs['bias_cat'] = torch.empty(4 * H, device=dev)
             self._packed = _lib.PolicyPacked(**{k: v.data_ptr() for k, v in self._bufs.items()})
         for p in ps:
             assert p.is_cuda and p.dtype == torch.float32 and p.is_contiguous()
@@ -137,9 +159,11 @@ class CommNetMLP(nn.Module):
         h2, c2 = torch.empty_like(h), torch.empty_like(c)
         value = torch.empty(B * N, 1, device=dev)
         logp = torch.empty(B, N, self._atot, device=dev)
+        ws, err = self.workspace(B)
         io = _lib.PolicyIO(x=xenc.data_ptr(), h=h.data_ptr(), c=c.data_ptr(), comm_action=_lib.ptr(comm),
                            alive=_lib.ptr(alive), fresh=None, tick=None, draws=None, h_out=h2.data_ptr(),
-                           c_out=c2.data_ptr(), value=value.data_ptr(), logp=logp.data_ptr(), action=None)
+                           c_out=c2.data_ptr(), value=value.data_ptr(), logp=logp.data_ptr(), action=None,
+                           workspace=_lib.ptr(ws), err=_lib.ptr(err))
         _lib.check(lib.ic3_policy_step(C.byref(cfg), C.byref(w), C.byref(io), _lib.stream()))
         action = list(torch.split(logp, list(self.args.naction_heads), dim=-1))
         return action, value, (h2, c2)

@@ -14,6 +14,8 @@
 #include <cstring>
 
 #include "ic3_common.cuh"
+#include "policy_heads.cuh"
+#include "policy_internal.h"
 
 namespace {
 
@@ -96,30 +98,6 @@ __device__ __forceinline__ void gemm_tile(const float (*A0)[H], const float (*A1
 }
 
 __device__ __forceinline__ float sigmoidf_(float v) { return 1.f / (1.f + expf(-v)); }
-
-// log-softmax + inverse-CDF sampling of one head; logits live one per lane
-// (lane off+a holds logit a).  Every lane of the warp executes this.
-__device__ __forceinline__ void head_logp_sample(float mylogit, int off, int na, int lane, float u, bool do_sample,
-                                                 float& mylogp, int& action) {
-  float m = -INFINITY;
-  for (int a = 0; a < na; ++a) m = fmaxf(m, __shfl_sync(IC3_FULL_MASK, mylogit, off + a));
-  float s = 0.f;
-  for (int a = 0; a < na; ++a) s += expf(__shfl_sync(IC3_FULL_MASK, mylogit, off + a) - m);
-  const float lse = m + logf(s);
-  mylogp = mylogit - lse;
-  action = na - 1;
-  if (do_sample) {
-    float cdf = 0.f;
-    bool found = false;
-    for (int a = 0; a < na; ++a) {
-      cdf += expf(__shfl_sync(IC3_FULL_MASK, mylogp, off + a));
-      if (!found && cdf > u) {
-        action = a;
-        found = true;
-      }
-    }
-  }
-}
 
 struct PolicyArgs {
   ic3_policy_cfg cfg;
@@ -249,42 +227,14 @@ __global__ void __launch_bounds__(NT) policy_step_kernel(PolicyArgs a) {
   __syncthreads();
 
   // ---- E: heads, log-softmax, sampling (comm.py:228-239, action_utils.py:32-36) --
-  int nout = 1, atot = 0;
-  for (int k = 0; k < cfg.nheads; ++k) atot += cfg.head_dim[k];
-  nout += atot;
   const int warp = ty, lane = tx;
   for (int r = warp; r < nrows; r += NT / 32) {
     float hv[H / 32];
 #pragma unroll
     for (int m = 0; m < H / 32; ++m) hv[m] = sm.h2[r][lane + 32 * m];
-    float mylogit = 0.f;
-    for (int o = 0; o < nout; ++o) {
-      float part = 0.f;
-#pragma unroll
-      for (int m = 0; m < H / 32; ++m) part = fmaf(hv[m], __ldg(a.w.head_w + (size_t)o * H + lane + 32 * m), part);
-#pragma unroll
-      for (int s = 16; s > 0; s >>= 1) part += __shfl_xor_sync(IC3_FULL_MASK, part, s);
-      if (lane == o) mylogit = part + __ldg(a.w.head_b + o);
-    }
-    const size_t grow = row0 + r;
     const int e = e0 + r / N, i = r - (r / N) * N;
-    if (lane == 0) io.value[grow] = mylogit;
-    uint4 w = make_uint4(0, 0, 0, 0);
-    const bool do_sample = io.action != nullptr;
-    if (do_sample && !io.draws)
-      w = ic3_draw24(cfg.seed, cfg.env_id0 + (uint32_t)e, io.tick ? io.tick[e] : 0u, IC3_STREAM_ACTION, (uint32_t)i);
-    int off = 1;
-    for (int k = 0; k < cfg.nheads; ++k) {
-      const int na = cfg.head_dim[k];
-      uint32_t u24 = 0;
-      if (do_sample) u24 = io.draws ? io.draws[grow * cfg.nheads + k] : ic3_word(w, k);
-      float mylogp;
-      int action;
-      head_logp_sample(mylogit, off, na, lane, (float)u24 * 5.9604644775390625e-08f, do_sample, mylogp, action);
-      if (lane >= off && lane < off + na) io.logp[grow * atot + (off - 1) + (lane - off)] = mylogp;
-      if (do_sample && lane == 0) io.action[grow * cfg.nheads + k] = action;
-      off += na;
-    }
+    heads_for_row<H>(cfg, a.w.head_w, a.w.head_b, hv, row0 + r, e, i, lane, io.tick, io.draws, io.value, io.logp,
+                     io.action);
   }
 }
 
@@ -602,8 +552,14 @@ extern "C" int ic3_policy_pack(const ic3_policy_cfg* cfg, const ic3_policy_param
     if (!p->head_w[k] || !p->head_b[k]) return IC3_E_NULL;
   pack_kernel<<<296, 256, 0, (cudaStream_t)stream>>>(*cfg, *p, *out);
   IC3_LAUNCH_CHECK();
+  if (out->lstm_img || out->bias_cat) {   // tensor-core operand images
+    if (!out->lstm_img || !out->bias_cat) return IC3_E_NULL;
+    return ic3_tc_pack(cfg, p, out, (cudaStream_t)stream);
+  }
   return IC3_OK;
 }
+
+extern "C" uint64_t ic3_policy_workspace_bytes(const ic3_policy_cfg* cfg) { return ic3_tc_workspace_bytes(cfg); }
 
 extern "C" int ic3_encoder_dense(const ic3_policy_cfg* cfg, const ic3_policy_packed* w, const float* obs,
                                  float* x, void* stream) {
@@ -668,6 +624,8 @@ extern "C" int ic3_policy_step(const ic3_policy_cfg* cfg, const ic3_policy_packe
   if (!io || !io->x || !io->h || !io->c || !io->h_out || !io->c_out || !io->value || !io->logp) return IC3_E_NULL;
   if (cfg->hard_attn && !io->comm_action) return IC3_E_NULL;
   if (cfg->N > ROWS) return IC3_E_RANGE;
+  if (io->workspace && w->lstm_img)       // tcgen05 path (policy_tc.cu); otherwise the fp32 SIMT kernel below
+    return ic3_tc_policy_step(cfg, w, io, (cudaStream_t)stream);
   PolicyArgs a{*cfg, *w, *io};
   IC3_DISPATCH_H(cfg->H, launch_policy<HH>(a, (cudaStream_t)stream));
 }

@@ -1,0 +1,9 @@
+// Internal (non-ABI) entry points of the tcgen05 policy path, called from policy.cu.
+#pragma once
+#include <cuda_runtime.h>
+
+#include "../../include/ic3net_b200.h"
+
+uint64_t ic3_tc_workspace_bytes(const ic3_policy_cfg* cfg);
+int ic3_tc_pack(const ic3_policy_cfg* cfg, const ic3_policy_params* p, const ic3_policy_packed* out, cudaStream_t s);
+int ic3_tc_policy_step(const ic3_policy_cfg* cfg, const ic3_policy_packed* w, const ic3_policy_io* io, cudaStream_t s);

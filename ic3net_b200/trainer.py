@@ -85,6 +85,7 @@ class Trainer(object):
         w = net.packed()
         hard = int(bool(args.hard_attn) and bool(args.commnet))
         s = _lib.stream()
+        ws, _ = net.workspace(B)          # tensor-core path scratch (None for the fp32 SIMT kernel)
         for t in range(T):
             if self.obs_mode == 'dense':
                 if self.is_tj:
@@ -102,7 +103,8 @@ class Trainer(object):
                                comm_action=b['comm'].data_ptr() if hard else None, alive=b['alive'].data_ptr(),
                                fresh=b['fresh'].data_ptr(), tick=e.tick.data_ptr(), draws=None,
                                h_out=b['h'].data_ptr(), c_out=b['c'].data_ptr(), value=b['value'][t].data_ptr(),
-                               logp=b['logp'][t].data_ptr(), action=b['action'][t].data_ptr())
+                               logp=b['logp'][t].data_ptr(), action=b['action'][t].data_ptr(),
+                               workspace=_lib.ptr(ws), err=b['err'].data_ptr())
             _lib.check(lib.ic3_policy_step(C.byref(cfg), C.byref(w), C.byref(io), s))
             r = _lib.RolloutIO(t=t, max_steps=args.max_steps, nheads=nh, hard_attn=hard,
                                comm_action_one=int(bool(args.comm_action_one)), last=int(t == T - 1),

@@ -210,7 +210,15 @@ typedef struct {
   float* lstm_b;   /* [4H]         b_ih + b_hh, column 4*u+gate */
   float* head_w;   /* [1+sum(na), H]  row 0 = value head, then heads in order */
   float* head_b;   /* [1+sum(na)] */
+  /* tcgen05 path (H == 128 only; both NULL selects the fp32 SIMT kernel):
+   * lstm_img: fp16 hi/lo split of 256 * [W_ih ; W_ih.C ; W_hh] (K = 384) as ready-made
+   *   shared-memory images, [2 column halves][12 K-chunks][hi,lo][core-matrix layout] = 786432 bytes;
+   * bias_cat: [4H] b_ih + b_hh + W_ih.c_b, column 4*u+gate. */
+  void* lstm_img;
+  float* bias_cat;
 } ic3_policy_packed;
+
+#define IC3_LSTM_IMG_BYTES 786432
 
 int ic3_policy_pack(const ic3_policy_cfg* cfg, const ic3_policy_params* p,
                     const ic3_policy_packed* out, void* stream);
@@ -239,7 +247,12 @@ typedef struct {
   float* value;               /* [B*N]    value_head (comm.py:228) */
   float* logp;                /* [B, N, sum(na)] log_softmax per head, heads concatenated (comm.py:239) */
   int32_t* action;            /* [B, N, nheads] sampled actions or NULL (action_utils.py:32-36) */
+  void* workspace;            /* tcgen05 path: ic3_policy_workspace_bytes(cfg) bytes of scratch (operand images), else NULL */
+  int32_t* err;               /* tcgen05 path: device flag word (pipeline watchdog), may be NULL */
 } ic3_policy_io;
+
+/* Scratch the tcgen05 policy path needs for a batch of cfg->B environments (0 when unsupported). */
+uint64_t ic3_policy_workspace_bytes(const ic3_policy_cfg* cfg);
 
 /* One CommNetMLP.forward (recurrent branch, comm_passes = 1) + select_action. */
 int ic3_policy_step(const ic3_policy_cfg* cfg, const ic3_policy_packed* w, const ic3_policy_io* io,

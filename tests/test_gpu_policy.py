@@ -25,25 +25,31 @@ def cpu(t):
     return t.detach().cpu().numpy()
 
 
+IMPLS = ["tc", "simt"]
+
+
 def build_net(meta_like, nagents, hid, obs_dim, heads, hard_attn, comm_mode="avg", comm_mask_zero=False,
-              comm_init="uniform", wseed=0, seed=0, env_id0=0):
+              comm_init="uniform", wseed=0, seed=0, env_id0=0, impl=None):
+    if impl == "tc" and hid != 128:
+        pytest.skip("tensor-core path is specialised for hid_size 128")
     from ic3net_b200.comm import CommNetMLP
     a = argparse.Namespace(nagents=nagents, hid_size=hid, comm_passes=1, recurrent=True, rnn_type="LSTM",
                            continuous=False, naction_heads=list(heads), comm_mask_zero=comm_mask_zero,
                            comm_mode=comm_mode, hard_attn=hard_attn, comm_init=comm_init, share_weights=False,
-                           seed=seed, env_id0=env_id0, commnet=True)
+                           seed=seed, env_id0=env_id0, commnet=True, policy_impl=impl)
     net = CommNetMLP(a, obs_dim)
     sd = make_weights(wseed, obs_dim, hid, heads, comm_init)
     net.load_state_dict({k: torch.from_numpy(v).float() for k, v in sd.items()})
     return net, a, sd
 
 
+@pytest.mark.parametrize("impl", IMPLS)
 @pytest.mark.parametrize("name", golden_names("fwd_"))
-def test_forward_matches_reference_golden(name):
+def test_forward_matches_reference_golden(name, impl):
     meta, z = load_golden(name)
     net, a, sd = build_net(meta, meta["nagents"], meta["hid_size"], meta["obs_dim"], meta["heads"],
                            meta["hard_attn"], meta["comm_mode"], meta["comm_mask_zero"], meta["comm_init"],
-                           wseed=meta["weights_seed"])
+                           wseed=meta["weights_seed"], impl=impl)
     assert sorted(net.state_dict().keys()) == sorted(sd.keys())      # checkpoint keys interchange
     dev = "cuda"
     for k in range(len(z["obs"])):
@@ -62,10 +68,11 @@ def test_forward_matches_reference_golden(name):
             assert close(cpu(act[j])[0], z["logp%d" % j][k]), name
 
 
-def test_forward_batched_mixed_masks():
-    """B = 77 envs (odd tile tail), per-env alive / comm masks, vs the float64 oracle."""
+@pytest.mark.parametrize("impl", IMPLS)
+def test_forward_batched_mixed_masks(impl):
+    """B = 77 envs (odd tile tail, envs straddling 128-row tiles), per-env alive / comm masks, vs the float64 oracle."""
     B, N, H, O, heads = 77, 10, 128, 61, (2, 2)
-    net, a, sd = build_net(None, N, H, O, heads, True, wseed=3)
+    net, a, sd = build_net(None, N, H, O, heads, True, wseed=3, impl=impl)
     p = opolicy.params_to_f64(sd)
     rs = np.random.RandomState(0)
     obs = (rs.rand(B, N, O) < 0.1) * rs.randint(1, 4, size=(B, N, O))
@@ -87,9 +94,10 @@ def test_forward_batched_mixed_masks():
 
 @pytest.mark.parametrize("H,N,O,heads", [(32, 3, 29, (5, 2)), (64, 5, 45, (5,)), (128, 20, 149, (2, 2)),
                                           (128, 32, 40, (3, 4, 2))])
-def test_forward_shapes(H, N, O, heads):
+@pytest.mark.parametrize("impl", IMPLS)
+def test_forward_shapes(H, N, O, heads, impl):
     B = 13
-    net, a, sd = build_net(None, N, H, O, heads, len(heads) > 1, wseed=H + N)
+    net, a, sd = build_net(None, N, H, O, heads, len(heads) > 1, wseed=H + N, impl=impl)
     p = opolicy.params_to_f64(sd)
     rs = np.random.RandomState(1)
     obs = rs.uniform(-1, 1, (B, N, O)) * (rs.rand(B, N, O) < 0.3)

@@ -25,14 +25,16 @@ def cpu(t):
     return t.detach().cpu().numpy()
 
 
-def build(meta, B, obs_mode="index", use_graph=False, seed=None, env_id0=0, **over):
+def build(meta, B, obs_mode="index", use_graph=False, seed=None, env_id0=0, impl=None, **over):
     from ic3net_b200 import data
     from ic3net_b200.comm import CommNetMLP
     from ic3net_b200.trainer import Trainer
     args = ns(meta["args"], nenvs=B, seed=meta["seed"] if seed is None else seed, env_id0=env_id0,
-              obs_mode=obs_mode, use_graph=use_graph, **over)
+              obs_mode=obs_mode, use_graph=use_graph, policy_impl=impl, **over)
     env = data.init(args.env_name, args)
     finish_args(args, env)
+    if impl == "tc" and args.hid_size != 128:
+        pytest.skip("tensor-core path is specialised for hid_size 128")
     net = CommNetMLP(args, args.num_inputs)
     sd = make_weights(meta["weights_seed"], args.num_inputs, args.hid_size, args.naction_heads, args.comm_init)
     net.load_state_dict({k: torch.from_numpy(v).float() for k, v in sd.items()})
@@ -41,11 +43,12 @@ def build(meta, B, obs_mode="index", use_graph=False, seed=None, env_id0=0, **ov
 
 @pytest.mark.parametrize("name", golden_names("ep_"))
 @pytest.mark.parametrize("obs_mode", ["index", "dense"])
-def test_first_episode_matches_reference_golden(name, obs_mode):
+@pytest.mark.parametrize("impl", ["tc", "simt"])
+def test_first_episode_matches_reference_golden(name, obs_mode, impl):
     meta, z = load_golden(name)
     ids = meta["env_ids"]
     B = max(ids) + 1
-    args, env, net, tr, p = build(meta, B, obs_mode)
+    args, env, net, tr, p = build(meta, B, obs_mode, impl=impl)
     T = args.max_steps
     batch = tr.rollout(T, meta["epoch"])
     torch.cuda.synchronize()
@@ -69,11 +72,12 @@ def test_first_episode_matches_reference_golden(name, obs_mode):
 @pytest.mark.parametrize("name,B,T", [("ep_pp_easy_ic3net", 11, 70), ("ep_tj_medium_ic3net", 7, 80),
                                       ("ep_tj_easy_ic3net", 9, 45), ("ep_pp_hard_commnet", 3, 90),
                                       ("ep_tj_medium_v1_commnet", 4, 50)])
-def test_lockstep_rollout_matches_oracle(name, B, T):
+@pytest.mark.parametrize("impl", ["tc", "simt"])
+def test_lockstep_rollout_matches_oracle(name, B, T, impl):
     """Every slot, every episode (auto-reset, cut at the batch end), teacher-forced with
     the GPU's own actions so both sides stay on one trajectory; plus the stat sums."""
     meta, z = load_golden(name)
-    args, env, net, tr, p = build(meta, B, "index", seed=321, env_id0=50)
+    args, env, net, tr, p = build(meta, B, "index", seed=321, env_id0=50, impl=impl)
     is_tj = args.env_name == "traffic_junction"
     batch = tr.rollout(T, 0)
     stat = tr.collect_stat()
