@@ -151,7 +151,8 @@ __global__ void __launch_bounds__(256) prep_kernel(ic3_policy_cfg cfg, ic3_polic
       const bool fr = io.fresh && io.fresh[e];
       xv = __ldg(reinterpret_cast<const float4*>(io.x + (size_t)row * TC_H) + q);
       if (!fr) hv = __ldg(reinterpret_cast<const float4*>(io.h + (size_t)row * TC_H) + q);
-      if (!cfg.comm_mask_zero && s_gate[r + 32] != 0.f) {
+      // episode start: every agent of the env has h = 0 (trainer.py:50-51), so S = 0 whatever the gates
+      if (!fr && !cfg.comm_mask_zero && s_gate[r + 32] != 0.f) {
         const long base = (long)e * N;
         for (int j = 0; j < N; ++j) {
           const long rj = base + j;
