@@ -38,10 +38,8 @@ constexpr int TC_NH = 256;              // gate columns per CTA (64 hidden units
 constexpr int A_CHUNK_BYTES = 2 * TC_M * TC_KC * 2;   // hi + lo = 16384
 constexpr int B_CHUNK_BYTES = 2 * TC_NH * TC_KC * 2;  // 32768
 constexpr int STAGE_BYTES = A_CHUNK_BYTES + B_CHUNK_BYTES;
-constexpr int NSTAGE = 2;
 constexpr int A_TILE_HALFS = TC_NCHUNK * A_CHUNK_BYTES / 2;   // 98304
 constexpr float SCALE_A = 16.f, SCALE_B = 256.f, INV_SCALE = 1.f / 4096.f;
-constexpr int TC_THREADS = 192;
 constexpr uint32_t WATCHDOG_SPINS = 1u << 22;
 
 // ---- image addressing (in halfs) ---------------------------------------------------------
@@ -108,21 +106,26 @@ __global__ void pack_tc_kernel(ic3_policy_params p, __half* __restrict__ img, fl
 }
 
 // ---- operand A image: x | S | h (every step) ---------------------------------------------------
-// One CTA per 128-row tile.  A warp item = 8 rows x 4 float4 columns, so every store instruction
-// writes two complete 128-byte core matrices.  Environments may straddle tiles: the gated sum of
-// comm.py:181-205 reads the other agents' rows straight from global memory (L1/L2 hits).
+// One CTA per 128-row tile.  Phase 1 forms, per environment touching the tile, the gated sum
+// T = sum_j g_j h_j (comm.py:181-205) in shared memory (environments may straddle tiles: their
+// other rows are read straight from global memory); phase 2 streams the tile: a warp item is
+// 8 rows x 4 float4 columns so every store instruction writes two complete 128-byte core
+// matrices, with S_k = g_k (T - h_k) / (n_alive - 1).
+constexpr int PREP_MAX_ENV = 66;   // environments touching a 128-row tile when N >= 2
+
 __global__ void __launch_bounds__(256) prep_kernel(ic3_policy_cfg cfg, ic3_policy_io io, __half* __restrict__ img) {
   __shared__ float s_gate[TC_M + 64];
   __shared__ float s_den[TC_M + 64];
+  __shared__ __align__(16) float s_T[PREP_MAX_ENV][TC_H];
   const int N = cfg.N;
-  const long R = (long)cfg.B * N;
+  const int R = cfg.B * N;
   const int tile = blockIdx.x;
-  const long row0 = (long)tile * TC_M;
+  const int row0 = tile * TC_M;
   for (int w = threadIdx.x; w < TC_M + 64; w += blockDim.x) {
-    const long row = row0 - 32 + w;
+    const int row = row0 - 32 + w;
     float g = 0.f, den = 1.f;
     if (row >= 0 && row < R) {
-      const int e = (int)(row / N), i = (int)(row - (long)e * N);
+      const int e = row / N, i = row - e * N;
       const bool fr = io.fresh && io.fresh[e];
       int n_alive = N, al = 1;
       if (io.alive && !fr) {                       // comm.py:102-104
@@ -132,43 +135,59 @@ __global__ void __launch_bounds__(256) prep_kernel(ic3_policy_cfg cfg, ic3_polic
       }
       int cm = 1;
       if (cfg.hard_attn) cm = fr ? 0 : (io.comm_action[(size_t)e * N + i] != 0);   // comm.py:171-175
-      g = (float)(al * cm);
+      // episode start: every agent of the env has h = 0 (trainer.py:50-51) -> nothing to send
+      g = fr ? 0.f : (float)(al * cm);
       if (cfg.comm_avg && n_alive > 1) den = (float)(n_alive - 1);                  // comm.py:194-196
     }
     s_gate[w] = g;
     s_den[w] = den;
   }
   __syncthreads();
+  const int e_first = row0 / N;
+  const int last_row = min(R, row0 + TC_M) - 1;
+  const bool want_s = !cfg.comm_mask_zero && N >= 2 && last_row >= row0;
+  if (want_s) {
+    const int nenv = last_row / N - e_first + 1;
+    for (int idx = threadIdx.x; idx < nenv * (TC_H / 4); idx += blockDim.x) {
+      const int el = idx >> 5, q = idx & 31;
+      const int base = (e_first + el) * N;
+      float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int j = 0; j < N; ++j) {
+        if (s_gate[base + j - row0 + 32] != 0.f) {
+          const float4 o = __ldg(reinterpret_cast<const float4*>(io.h + (size_t)(base + j) * TC_H) + q);
+          t.x += o.x; t.y += o.y; t.z += o.z; t.w += o.w;
+        }
+      }
+      *reinterpret_cast<float4*>(&s_T[el][4 * q]) = t;
+    }
+  }
+  __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  const size_t tile_base = (size_t)tile * A_TILE_HALFS;
   for (int item = warp; item < 128; item += 8) {
     const int rc = item & 15, qg = item >> 4;
-    const int r = rc * 8 + (lane & 7), q = qg * 4 + (lane >> 3);
-    const long row = row0 + r;
+    const int r8 = lane & 7, q = qg * 4 + (lane >> 3);
+    const int r = rc * 8 + r8;
+    const int row = row0 + r;
     float4 xv = zero4, hv = zero4, sv = zero4;
     if (row < R) {
-      const int e = (int)(row / N);
+      const int e = row / N;
       const bool fr = io.fresh && io.fresh[e];
       xv = __ldg(reinterpret_cast<const float4*>(io.x + (size_t)row * TC_H) + q);
       if (!fr) hv = __ldg(reinterpret_cast<const float4*>(io.h + (size_t)row * TC_H) + q);
-      // episode start: every agent of the env has h = 0 (trainer.py:50-51), so S = 0 whatever the gates
-      if (!fr && !cfg.comm_mask_zero && s_gate[r + 32] != 0.f) {
-        const long base = (long)e * N;
-        for (int j = 0; j < N; ++j) {
-          const long rj = base + j;
-          if (rj != row && s_gate[(int)(rj - row0) + 32] != 0.f) {
-            const float4 o = __ldg(reinterpret_cast<const float4*>(io.h + (size_t)rj * TC_H) + q);
-            sv.x += o.x; sv.y += o.y; sv.z += o.z; sv.w += o.w;
-          }
-        }
-        const float d = s_den[r + 32];
-        sv.x /= d; sv.y /= d; sv.z /= d; sv.w /= d;
+      if (want_s && s_gate[r + 32] != 0.f) {       // gate 1 => own h is part of T
+        const float4 t = *reinterpret_cast<const float4*>(&s_T[e - e_first][4 * q]);
+        const float inv = 1.f / s_den[r + 32];
+        sv.x = (t.x - hv.x) * inv; sv.y = (t.y - hv.y) * inv; sv.z = (t.z - hv.z) * inv; sv.w = (t.w - hv.w) * inv;
       }
     }
-    const int k = 4 * q;
-    store_split4(img, a_img_off(tile, k, r, 0), a_img_off(tile, k, r, 1), xv, SCALE_A);
-    store_split4(img, a_img_off(tile, TC_H + k, r, 0), a_img_off(tile, TC_H + k, r, 1), sv, SCALE_A);
-    store_split4(img, a_img_off(tile, 2 * TC_H + k, r, 0), a_img_off(tile, 2 * TC_H + k, r, 1), hv, SCALE_A);
+    // k = sec*128 + 4q  ->  chunk = sec*4 + (q >> 3), kcore = (q & 7) >> 1, k8 = 4 * (q & 1)
+    const size_t cell = tile_base + (size_t)((((q & 7) >> 1) * 16 + rc) * 64 + r8 * 8 + (q & 1) * 4);
+    const int c = q >> 3;
+    store_split4(img, cell + (size_t)((0 * 4 + c) * 2 + 0) * 4096, cell + (size_t)((0 * 4 + c) * 2 + 1) * 4096, xv, SCALE_A);
+    store_split4(img, cell + (size_t)((1 * 4 + c) * 2 + 0) * 4096, cell + (size_t)((1 * 4 + c) * 2 + 1) * 4096, sv, SCALE_A);
+    store_split4(img, cell + (size_t)((2 * 4 + c) * 2 + 0) * 4096, cell + (size_t)((2 * 4 + c) * 2 + 1) * 4096, hv, SCALE_A);
   }
 }
 
@@ -236,30 +255,55 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
-__device__ __forceinline__ float sigmoid_(float v) { return 1.f / (1.f + expf(-v)); }
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+
+// Gate non-linearities on the SFU: ex2.approx (2^-22 rel.) + rcp.approx (1 ulp); both well inside
+// the 1e-5 budget of the hidden state (tests/test_gpu_policy.py, tests/test_gpu_rollout.py).
+__device__ __forceinline__ float sigmoid_fast(float v) { return __fdividef(1.f, 1.f + __expf(-v)); }
+__device__ __forceinline__ float tanh_fast(float v) {
+  const float e = __expf(-2.f * fabsf(v));                 // in (0, 1]: no overflow
+  return copysignf(__fdividef(1.f - e, 1.f + e), v);
+}
 
 // ---- the tensor-core kernel -----------------------------------------------------------------------
-__global__ void __launch_bounds__(TC_THREADS) lstm_tc_kernel(ic3_policy_cfg cfg, ic3_policy_io io,
-                                                             const __half* __restrict__ a_img,
-                                                             const __half* __restrict__ b_img,
-                                                             const float* __restrict__ bias_cat) {
+// Persistent, one CTA per SM, warp-specialised:
+//   warp 8  producer   ring of NSTAGE (A 16 KB + B 32 KB) stages filled by cp.async.bulk, running
+//                      ahead across work items
+//   warp 9  MMA        one thread issues 3 x tcgen05.mma (128 x 256 x 16) per k-step into one of
+//                      two 256-column TMEM accumulators
+//   warps 0-7 epilogue warp w owns TMEM lanes 32*(w%4).. and columns 128*(w/4)..: LSTM cell of item i
+//                      overlaps the MMAs of item i+1
+// Work item = (128-row tile, 256-column half); item 2t and 2t+1 share the A tile (second read hits L2).
+constexpr int NSTAGE_P = 4;
+constexpr int TC_P_THREADS = 320;
+constexpr int EPI_THREADS = 256;
+
+__global__ void __launch_bounds__(TC_P_THREADS, 1) lstm_tc_kernel(ic3_policy_cfg cfg, ic3_policy_io io,
+                                                                 const __half* __restrict__ a_img,
+                                                                 const __half* __restrict__ b_img,
+                                                                 const float* __restrict__ bias_cat, int nitems) {
   extern __shared__ __align__(1024) unsigned char smem[];
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + NSTAGE * STAGE_BYTES);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
-  const uint32_t bar_full = smem_u32(bars), bar_empty = smem_u32(bars + NSTAGE), bar_tmem = smem_u32(bars + 2 * NSTAGE);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + NSTAGE_P * STAGE_BYTES);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
+  const uint32_t bar_full = smem_u32(bars), bar_empty = smem_u32(bars + NSTAGE_P);
+  const uint32_t bar_tfull = smem_u32(bars + 2 * NSTAGE_P), bar_tempty = smem_u32(bars + 2 * NSTAGE_P + 2);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int tile = blockIdx.x >> 1, nh = blockIdx.x & 1;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < NSTAGE; ++s) {
+    for (int s = 0; s < NSTAGE_P; ++s) {
       mbar_init(bar_full + 8 * s, 1);
       mbar_init(bar_empty + 8 * s, 1);
     }
-    mbar_init(bar_tmem, 1);
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(bar_tfull + 8 * a, 1);
+      mbar_init(bar_tempty + 8 * a, EPI_THREADS);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 4) {   // TMEM: 256 fp32 columns x 128 lanes for the accumulator tile
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TC_NH)
+  if (warp == 8) {   // all 512 TMEM columns: two 128-lane x 256-column fp32 accumulators
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -268,95 +312,175 @@ __global__ void __launch_bounds__(TC_THREADS) lstm_tc_kernel(ic3_policy_cfg cfg,
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 4 && lane == 0) {
-    // ===== producer: two bulk copies per stage =====
-    const unsigned char* a_src = reinterpret_cast<const unsigned char*>(a_img) + (size_t)tile * TC_NCHUNK * A_CHUNK_BYTES;
-    const unsigned char* b_src = reinterpret_cast<const unsigned char*>(b_img) + (size_t)nh * TC_NCHUNK * B_CHUNK_BYTES;
-    for (int c = 0; c < TC_NCHUNK; ++c) {
-      const int s = c & (NSTAGE - 1);
-      if (!mbar_wait(bar_empty + 8 * s, ((c / NSTAGE) & 1) ^ 1, io.err)) break;
-      const uint32_t dst = smem_u32(smem + s * STAGE_BYTES);
-      mbar_expect_tx(bar_full + 8 * s, STAGE_BYTES);
-      bulk_g2s(dst, a_src + (size_t)c * A_CHUNK_BYTES, A_CHUNK_BYTES, bar_full + 8 * s);
-      bulk_g2s(dst + A_CHUNK_BYTES, b_src + (size_t)c * B_CHUNK_BYTES, B_CHUNK_BYTES, bar_full + 8 * s);
+  if (warp == 8 && lane == 0) {
+    // ===== producer =====
+    uint32_t g = 0;
+    bool ok = true;
+    for (int item = blockIdx.x; item < nitems && ok; item += gridDim.x) {
+      const int tile = item >> 1, nh = item & 1;
+      const unsigned char* a_src = reinterpret_cast<const unsigned char*>(a_img) + (size_t)tile * TC_NCHUNK * A_CHUNK_BYTES;
+      const unsigned char* b_src = reinterpret_cast<const unsigned char*>(b_img) + (size_t)nh * TC_NCHUNK * B_CHUNK_BYTES;
+      for (int c = 0; c < TC_NCHUNK && ok; ++c, ++g) {
+        const uint32_t s = g % NSTAGE_P;
+        ok = mbar_wait(bar_empty + 8 * s, ((g / NSTAGE_P) & 1) ^ 1, io.err);
+        const uint32_t dst = smem_u32(smem + s * STAGE_BYTES);
+        mbar_expect_tx(bar_full + 8 * s, STAGE_BYTES);
+        bulk_g2s(dst, a_src + (size_t)c * A_CHUNK_BYTES, A_CHUNK_BYTES, bar_full + 8 * s);
+        bulk_g2s(dst + A_CHUNK_BYTES, b_src + (size_t)c * B_CHUNK_BYTES, B_CHUNK_BYTES, bar_full + 8 * s);
+      }
     }
-  } else if (warp == 5 && lane == 0) {
-    // ===== MMA issuer: 3 x (128 x 256 x 16) per k-step, 72 instructions per tile =====
+  } else if (warp == 9 && lane == 0) {
+    // ===== MMA issuer =====
     // instruction descriptor: D = f32 (bits 4-5 = 1), A = B = f16 (0), K-major both, N >> 3 at 17, M >> 4 at 24
     const uint32_t idesc = (1u << 4) | ((uint32_t)(TC_NH >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
+    uint32_t g = 0, li = 0;
     bool ok = true;
-    for (int c = 0; c < TC_NCHUNK && ok; ++c) {
-      const int s = c & (NSTAGE - 1);
-      ok = mbar_wait(bar_full + 8 * s, (c / NSTAGE) & 1, io.err);
+    for (int item = blockIdx.x; item < nitems && ok; item += gridDim.x, ++li) {
+      const uint32_t acc = li & 1;
+      ok = mbar_wait(bar_tempty + 8 * acc, ((li >> 1) & 1) ^ 1, io.err);   // epilogue drained this accumulator
       tc_fence_after();
-      const uint32_t a0 = smem_u32(smem + s * STAGE_BYTES), b0 = a0 + A_CHUNK_BYTES;
+      const uint32_t tmem_d = tmem_base + acc * TC_NH;
+      for (int c = 0; c < TC_NCHUNK && ok; ++c, ++g) {
+        const uint32_t s = g % NSTAGE_P;
+        ok = mbar_wait(bar_full + 8 * s, (g / NSTAGE_P) & 1, io.err);
+        tc_fence_after();
+        const uint32_t a0 = smem_u32(smem + s * STAGE_BYTES), b0 = a0 + A_CHUNK_BYTES;
 #pragma unroll
-      for (int ks = 0; ks < TC_KC / 16; ++ks) {
-        // A: kcore block = 16 rcores x 128 B = 2048 B; B: 32 ncores x 128 B = 4096 B; lo half follows hi half
-        const uint64_t da_hi = make_desc(a0 + ks * 4096, 2048, 128);
-        const uint64_t da_lo = make_desc(a0 + A_CHUNK_BYTES / 2 + ks * 4096, 2048, 128);
-        const uint64_t db_hi = make_desc(b0 + ks * 8192, 4096, 128);
-        const uint64_t db_lo = make_desc(b0 + B_CHUNK_BYTES / 2 + ks * 8192, 4096, 128);
-        tc_mma_f16(tmem_base, da_hi, db_hi, idesc, (c | ks) != 0);
-        tc_mma_f16(tmem_base, da_lo, db_hi, idesc, 1);
-        tc_mma_f16(tmem_base, da_hi, db_lo, idesc, 1);
-      }
-      tc_commit(bar_empty + 8 * s);      // frees the stage when these MMAs have read it
-    }
-    tc_commit(bar_tmem);                 // accumulator complete
-  } else if (warp < 4) {
-    // ===== epilogue: thread = one row of the tile (TMEM lane), 4 hidden units per tcgen05.ld =====
-    const bool ok = mbar_wait(bar_tmem, 0, io.err);
-    tc_fence_after();
-    const int r = warp * 32 + lane;
-    const long row = (long)tile * TC_M + r;
-    const long R = (long)cfg.B * cfg.N;
-    const bool valid = ok && row < R;
-    bool fr = false;
-    if (valid && io.fresh) fr = io.fresh[row / cfg.N] != 0;
-    const uint32_t tlane = tmem_base + ((uint32_t)(warp * 32) << 16);
-    for (int cg = 0; cg < TC_NH / 16; ++cg) {
-      uint32_t v[16];
-      tmem_ld16(tlane + cg * 16, v);
-      if (valid) {
-        const int u0 = nh * (TC_NH / 4) + cg * 4;
-        float4 cold = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (!fr) cold = *reinterpret_cast<const float4*>(io.c + (size_t)row * TC_H + u0);
-        float cn[4], hn[4];
-        const float co[4] = {cold.x, cold.y, cold.z, cold.w};
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const float4 b = __ldg(reinterpret_cast<const float4*>(bias_cat) + (u0 + j));
-          const float gi = sigmoid_(fmaf(__uint_as_float(v[4 * j + 0]), INV_SCALE, b.x));
-          const float gf = sigmoid_(fmaf(__uint_as_float(v[4 * j + 1]), INV_SCALE, b.y));
-          const float gg = tanhf(fmaf(__uint_as_float(v[4 * j + 2]), INV_SCALE, b.z));
-          const float go = sigmoid_(fmaf(__uint_as_float(v[4 * j + 3]), INV_SCALE, b.w));
-          cn[j] = gf * co[j] + gi * gg;
-          hn[j] = go * tanhf(cn[j]);
+        for (int ks = 0; ks < TC_KC / 16; ++ks) {
+          // A: kcore block = 16 rcores x 128 B = 2048 B; B: 32 ncores x 128 B = 4096 B; lo half follows hi half
+          const uint64_t da_hi = make_desc(a0 + ks * 4096, 2048, 128);
+          const uint64_t da_lo = make_desc(a0 + A_CHUNK_BYTES / 2 + ks * 4096, 2048, 128);
+          const uint64_t db_hi = make_desc(b0 + ks * 8192, 4096, 128);
+          const uint64_t db_lo = make_desc(b0 + B_CHUNK_BYTES / 2 + ks * 8192, 4096, 128);
+          tc_mma_f16(tmem_d, da_hi, db_hi, idesc, (c | ks) != 0);
+          tc_mma_f16(tmem_d, da_lo, db_hi, idesc, 1);
+          tc_mma_f16(tmem_d, da_hi, db_lo, idesc, 1);
         }
-        *reinterpret_cast<float4*>(io.c_out + (size_t)row * TC_H + u0) = make_float4(cn[0], cn[1], cn[2], cn[3]);
-        *reinterpret_cast<float4*>(io.h_out + (size_t)row * TC_H + u0) = make_float4(hn[0], hn[1], hn[2], hn[3]);
+        tc_commit(bar_empty + 8 * s);      // frees the stage when these MMAs have read it
       }
+      tc_commit(bar_tfull + 8 * acc);      // accumulator complete
+    }
+  } else if (warp < 8) {
+    // ===== epilogue: thread = (row of the tile, 32 hidden units) =====
+    const int quarter = warp & 3, chalf = warp >> 2;
+    const int r = quarter * 32 + lane;
+    const int R = cfg.B * cfg.N;
+    uint32_t li = 0;
+    bool ok = true;
+    for (int item = blockIdx.x; item < nitems; item += gridDim.x, ++li) {
+      const int tile = item >> 1, nh = item & 1;
+      const uint32_t acc = li & 1;
+      if (ok) ok = mbar_wait(bar_tfull + 8 * acc, (li >> 1) & 1, io.err);
+      tc_fence_after();
+      const int row = tile * TC_M + r;
+      const bool valid = ok && row < R;
+      bool fr = false;
+      if (valid && io.fresh) fr = io.fresh[row / cfg.N] != 0;
+      const uint32_t taddr = tmem_base + acc * TC_NH + chalf * 128 + ((uint32_t)(quarter * 32) << 16);
+#pragma unroll 2
+      for (int cg = 0; cg < 8; ++cg) {
+        uint32_t v[16];
+        tmem_ld16(taddr + cg * 16, v);
+        if (valid) {
+          const int u0 = nh * (TC_NH / 4) + chalf * 32 + cg * 4;
+          float4 cold = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (!fr) cold = *reinterpret_cast<const float4*>(io.c + (size_t)row * TC_H + u0);
+          float cn[4], hn[4];
+          const float co[4] = {cold.x, cold.y, cold.z, cold.w};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float4 b = __ldg(reinterpret_cast<const float4*>(bias_cat) + (u0 + j));
+            const float gi = sigmoid_fast(fmaf(__uint_as_float(v[4 * j + 0]), INV_SCALE, b.x));
+            const float gf = sigmoid_fast(fmaf(__uint_as_float(v[4 * j + 1]), INV_SCALE, b.y));
+            const float gg = tanh_fast(fmaf(__uint_as_float(v[4 * j + 2]), INV_SCALE, b.z));
+            const float go = sigmoid_fast(fmaf(__uint_as_float(v[4 * j + 3]), INV_SCALE, b.w));
+            cn[j] = fmaf(gf, co[j], gi * gg);
+            hn[j] = go * tanh_fast(cn[j]);
+          }
+          *reinterpret_cast<float4*>(io.c_out + (size_t)row * TC_H + u0) = make_float4(cn[0], cn[1], cn[2], cn[3]);
+          *reinterpret_cast<float4*>(io.h_out + (size_t)row * TC_H + u0) = make_float4(hn[0], hn[1], hn[2], hn[3]);
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(bar_tempty + 8 * acc);   // this thread no longer reads the accumulator
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 4) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TC_NH) : "memory");
+  if (warp == 8) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
   }
 }
 
 // ---- heads + sampling from h' (comm.py:228-239, action_utils.py:32-36) -----------------------------
+// P lanes per agent row (P = pow2 >= 1 + sum(na)), lane o of a group computes output o as a full
+// 128-long dot product (h row broadcast inside the group, weight rows L1-resident), then the
+// log-softmax / inverse-CDF sampling runs inside the group with width-P shuffles.
+template <int P>
 __global__ void __launch_bounds__(256) heads_kernel(ic3_policy_cfg cfg, ic3_policy_packed w, ic3_policy_io io) {
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const long row = (long)blockIdx.x * 8 + warp;
-  if (row >= (long)cfg.B * cfg.N) return;
-  float hv[TC_H / 32];
-#pragma unroll
-  for (int m = 0; m < TC_H / 32; ++m) hv[m] = io.h_out[(size_t)row * TC_H + lane + 32 * m];
-  const int e = (int)(row / cfg.N), i = (int)(row - (long)e * cfg.N);
-  heads_for_row<TC_H>(cfg, w.head_w, w.head_b, hv, (size_t)row, e, i, lane, io.tick, io.draws, io.value, io.logp,
-                      io.action);
+  constexpr int RPW = 32 / P;
+  const int lane = threadIdx.x & 31, o = lane % P;
+  const long R = (long)cfg.B * cfg.N;
+  const long row = ((long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * RPW + lane / P;
+  const bool live = row < R;
+  int atot = 0;
+  for (int k = 0; k < cfg.nheads; ++k) atot += cfg.head_dim[k];
+  const int nout = 1 + atot;
+  float logit = 0.f;
+  if (live && o < nout) {
+    const float4* hp = reinterpret_cast<const float4*>(io.h_out + (size_t)row * TC_H);
+    const float4* wp = reinterpret_cast<const float4*>(w.head_w + (size_t)o * TC_H);
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll 8
+    for (int q = 0; q < TC_H / 4; ++q) {
+      const float4 hv = hp[q];
+      const float4 wv = __ldg(wp + q);
+      a0 = fmaf(hv.x, wv.x, a0); a1 = fmaf(hv.y, wv.y, a1); a2 = fmaf(hv.z, wv.z, a2); a3 = fmaf(hv.w, wv.w, a3);
+    }
+    logit = (a0 + a1) + (a2 + a3) + __ldg(w.head_b + o);
+  }
+  if (live && o == 0) io.value[row] = logit;
+  const bool do_sample = io.action != nullptr;
+  const int e = live ? (int)(row / cfg.N) : 0, i = live ? (int)(row - (long)e * cfg.N) : 0;
+  uint32_t w0 = 0, w1 = 0, w2 = 0, w3 = 0;
+  if (do_sample && !io.draws) {
+    if (o == 0 && live) {
+      const uint4 d = ic3_draw24(cfg.seed, cfg.env_id0 + (uint32_t)e, io.tick ? io.tick[e] : 0u, IC3_STREAM_ACTION, (uint32_t)i);
+      w0 = d.x; w1 = d.y; w2 = d.z; w3 = d.w;
+    }
+    w0 = __shfl_sync(IC3_FULL_MASK, w0, 0, P); w1 = __shfl_sync(IC3_FULL_MASK, w1, 0, P);
+    w2 = __shfl_sync(IC3_FULL_MASK, w2, 0, P); w3 = __shfl_sync(IC3_FULL_MASK, w3, 0, P);
+  }
+  int off = 1;
+  for (int k = 0; k < cfg.nheads; ++k) {
+    const int na = cfg.head_dim[k];
+    float m = -INFINITY;
+    for (int a = 0; a < na; ++a) m = fmaxf(m, __shfl_sync(IC3_FULL_MASK, logit, off + a, P));
+    float s = 0.f;
+    for (int a = 0; a < na; ++a) s += expf(__shfl_sync(IC3_FULL_MASK, logit, off + a, P) - m);
+    const float mylogp = logit - (m + logf(s));
+    uint32_t u24 = 0;
+    if (do_sample) {
+      if (io.draws) u24 = live ? io.draws[(size_t)row * cfg.nheads + k] : 0u;
+      else u24 = k == 0 ? w0 : (k == 1 ? w1 : (k == 2 ? w2 : w3));
+    }
+    const float u = (float)u24 * 5.9604644775390625e-08f;
+    int act = na - 1;
+    if (do_sample) {
+      float cdf = 0.f;
+      bool found = false;
+      for (int a = 0; a < na; ++a) {
+        cdf += expf(__shfl_sync(IC3_FULL_MASK, mylogp, off + a, P));
+        if (!found && cdf > u) {
+          act = a;
+          found = true;
+        }
+      }
+    }
+    if (live && o >= off && o < off + na) io.logp[(size_t)row * atot + (off - 1) + (o - off)] = mylogp;
+    if (live && do_sample && o == 0) io.action[(size_t)row * cfg.nheads + k] = act;
+    off += na;
+  }
 }
 
 }  // namespace
@@ -384,17 +508,29 @@ int ic3_tc_policy_step(const ic3_policy_cfg* cfg, const ic3_policy_packed* w, co
   __half* img = reinterpret_cast<__half*>(io->workspace);
   prep_kernel<<<ntiles, 256, 0, s>>>(*cfg, *io, img);
   IC3_LAUNCH_CHECK();
-  const size_t smem = NSTAGE * STAGE_BYTES + 128;
-  static bool configured = false;
-  if (!configured) {
+  const size_t smem = NSTAGE_P * STAGE_BYTES + 256;
+  static int num_sms = 0;
+  if (num_sms == 0) {
     cudaError_t e = cudaFuncSetAttribute(lstm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
-    configured = true;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    e = cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (e != cudaSuccess || num_sms <= 0) return e != cudaSuccess ? (int)e : IC3_E_RANGE;
   }
-  lstm_tc_kernel<<<2 * ntiles, TC_THREADS, smem, s>>>(*cfg, *io, img, reinterpret_cast<const __half*>(w->lstm_img),
-                                                      w->bias_cat);
+  const int nitems = 2 * ntiles;
+  const int grid = nitems < num_sms ? nitems : num_sms;
+  lstm_tc_kernel<<<grid, TC_P_THREADS, smem, s>>>(*cfg, *io, img, reinterpret_cast<const __half*>(w->lstm_img),
+                                                   w->bias_cat, nitems);
   IC3_LAUNCH_CHECK();
-  heads_kernel<<<(int)((R + 7) / 8), 256, 0, s>>>(*cfg, *w, *io);
+  int nout = 1;
+  for (int k = 0; k < cfg->nheads; ++k) nout += cfg->head_dim[k];
+  const int P = nout <= 8 ? 8 : (nout <= 16 ? 16 : 32);
+  const long rows_per_block = 8L * (32 / P);
+  const int hgrid = (int)((R + rows_per_block - 1) / rows_per_block);
+  if (P == 8) heads_kernel<8><<<hgrid, 256, 0, s>>>(*cfg, *w, *io);
+  else if (P == 16) heads_kernel<16><<<hgrid, 256, 0, s>>>(*cfg, *w, *io);
+  else heads_kernel<32><<<hgrid, 256, 0, s>>>(*cfg, *w, *io);
   IC3_LAUNCH_CHECK();
   return IC3_OK;
 }
