@@ -111,17 +111,18 @@ __global__ void pack_tc_kernel(ic3_policy_params p, __half* __restrict__ img, fl
 // other rows are read straight from global memory); phase 2 streams the tile: a warp item is
 // 8 rows x 4 float4 columns so every store instruction writes two complete 128-byte core
 // matrices, with S_k = g_k (T - h_k) / (n_alive - 1).
-constexpr int PREP_MAX_ENV = 66;   // environments touching a 128-row tile when N >= 2
+constexpr int PREP_ROWS = 64;      // rows per CTA (half a tile): 2 x more CTAs in flight than tiles
+constexpr int PREP_MAX_ENV = 34;   // environments touching 64 rows when N >= 2
 
 __global__ void __launch_bounds__(256) prep_kernel(ic3_policy_cfg cfg, ic3_policy_io io, __half* __restrict__ img) {
-  __shared__ float s_gate[TC_M + 64];
-  __shared__ float s_den[TC_M + 64];
+  __shared__ float s_gate[PREP_ROWS + 64];
+  __shared__ float s_den[PREP_ROWS + 64];
   __shared__ __align__(16) float s_T[PREP_MAX_ENV][TC_H];
   const int N = cfg.N;
   const int R = cfg.B * N;
-  const int tile = blockIdx.x;
-  const int row0 = tile * TC_M;
-  for (int w = threadIdx.x; w < TC_M + 64; w += blockDim.x) {
+  const int tile = blockIdx.x >> 1, hb = blockIdx.x & 1;
+  const int row0 = tile * TC_M + hb * PREP_ROWS;
+  for (int w = threadIdx.x; w < PREP_ROWS + 64; w += blockDim.x) {
     const int row = row0 - 32 + w;
     float g = 0.f, den = 1.f;
     if (row >= 0 && row < R) {
@@ -144,7 +145,7 @@ __global__ void __launch_bounds__(256) prep_kernel(ic3_policy_cfg cfg, ic3_polic
   }
   __syncthreads();
   const int e_first = row0 / N;
-  const int last_row = min(R, row0 + TC_M) - 1;
+  const int last_row = min(R, row0 + PREP_ROWS) - 1;
   const bool want_s = !cfg.comm_mask_zero && N >= 2 && last_row >= row0;
   if (want_s) {
     const int nenv = last_row / N - e_first + 1;
@@ -165,20 +166,22 @@ __global__ void __launch_bounds__(256) prep_kernel(ic3_policy_cfg cfg, ic3_polic
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
   const size_t tile_base = (size_t)tile * A_TILE_HALFS;
-  for (int item = warp; item < 128; item += 8) {
-    const int rc = item & 15, qg = item >> 4;
+#pragma unroll 2
+  for (int item = warp; item < 64; item += 8) {
+    const int rcl = item & 7, qg = item >> 3;
     const int r8 = lane & 7, q = qg * 4 + (lane >> 3);
-    const int r = rc * 8 + r8;
-    const int row = row0 + r;
+    const int rl = rcl * 8 + r8;                 // row inside this CTA's 64 rows
+    const int rc = hb * 8 + rcl;                 // 8-row group inside the 128-row tile
+    const int row = row0 + rl;
     float4 xv = zero4, hv = zero4, sv = zero4;
     if (row < R) {
       const int e = row / N;
       const bool fr = io.fresh && io.fresh[e];
       xv = __ldg(reinterpret_cast<const float4*>(io.x + (size_t)row * TC_H) + q);
       if (!fr) hv = __ldg(reinterpret_cast<const float4*>(io.h + (size_t)row * TC_H) + q);
-      if (want_s && s_gate[r + 32] != 0.f) {       // gate 1 => own h is part of T
+      if (want_s && s_gate[rl + 32] != 0.f) {      // gate 1 => own h is part of T
         const float4 t = *reinterpret_cast<const float4*>(&s_T[e - e_first][4 * q]);
-        const float inv = 1.f / s_den[r + 32];
+        const float inv = 1.f / s_den[rl + 32];
         sv.x = (t.x - hv.x) * inv; sv.y = (t.y - hv.y) * inv; sv.z = (t.z - hv.z) * inv; sv.w = (t.w - hv.w) * inv;
       }
     }
@@ -426,18 +429,27 @@ __global__ void __launch_bounds__(256) heads_kernel(ic3_policy_cfg cfg, ic3_poli
   int atot = 0;
   for (int k = 0; k < cfg.nheads; ++k) atot += cfg.head_dim[k];
   const int nout = 1 + atot;
+  // head weights k-major in shared memory: the P lanes of a group read P consecutive floats,
+  // every group reads the same addresses -> one broadcast wavefront per load
+  __shared__ float s_w[TC_H * P];
+  for (int idx = threadIdx.x; idx < TC_H * P; idx += blockDim.x) {
+    const int k = idx / P, oo = idx - k * P;
+    s_w[idx] = oo < nout ? __ldg(w.head_w + (size_t)oo * TC_H + k) : 0.f;
+  }
+  __syncthreads();
   float logit = 0.f;
-  if (live && o < nout) {
+  if (live) {
     const float4* hp = reinterpret_cast<const float4*>(io.h_out + (size_t)row * TC_H);
-    const float4* wp = reinterpret_cast<const float4*>(w.head_w + (size_t)o * TC_H);
     float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
 #pragma unroll 8
     for (int q = 0; q < TC_H / 4; ++q) {
       const float4 hv = hp[q];
-      const float4 wv = __ldg(wp + q);
-      a0 = fmaf(hv.x, wv.x, a0); a1 = fmaf(hv.y, wv.y, a1); a2 = fmaf(hv.z, wv.z, a2); a3 = fmaf(hv.w, wv.w, a3);
+      a0 = fmaf(hv.x, s_w[(4 * q + 0) * P + o], a0);
+      a1 = fmaf(hv.y, s_w[(4 * q + 1) * P + o], a1);
+      a2 = fmaf(hv.z, s_w[(4 * q + 2) * P + o], a2);
+      a3 = fmaf(hv.w, s_w[(4 * q + 3) * P + o], a3);
     }
-    logit = (a0 + a1) + (a2 + a3) + __ldg(w.head_b + o);
+    logit = (a0 + a1) + (a2 + a3) + (o < nout ? __ldg(w.head_b + o) : 0.f);
   }
   if (live && o == 0) io.value[row] = logit;
   const bool do_sample = io.action != nullptr;
@@ -506,7 +518,7 @@ int ic3_tc_policy_step(const ic3_policy_cfg* cfg, const ic3_policy_packed* w, co
   const long R = (long)cfg->B * cfg->N;
   const int ntiles = (int)((R + TC_M - 1) / TC_M);
   __half* img = reinterpret_cast<__half*>(io->workspace);
-  prep_kernel<<<ntiles, 256, 0, s>>>(*cfg, *io, img);
+  prep_kernel<<<2 * ntiles, 256, 0, s>>>(*cfg, *io, img);
   IC3_LAUNCH_CHECK();
   const size_t smem = NSTAGE_P * STAGE_BYTES + 256;
   static int num_sms = 0;
