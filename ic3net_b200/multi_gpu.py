@@ -1,0 +1,119 @@
+"""Data-parallel trainer: the B200 replacement of the reference's ``multi_processing.py``.
+
+Reference (multi_processing.py:41-104): N forked processes share the parameters, each runs
+``run_batch`` + ``compute_grad`` on its own environment, the master sums the per-process
+gradients through shared memory, divides by the GLOBAL number of env steps and takes one
+RMSprop step (:90-97); ``stat`` dicts are merged with ``merge_stat`` (:86-88).
+
+Here: one process per GPU (``torch.distributed``; NCCL over NVLink on GPUs, gloo in the CPU
+tests), parameters replicated, environment slots sharded (rank r owns global env ids
+``[r*B, (r+1)*B)``, i.e. ``args.env_id0 = rank * args.nenvs`` selects its Philox streams).
+Per update exactly ONE gradient collective: an all-reduce(sum) of the flat fp32 gradient
+buffer (parameters without a gradient -- ``hidd_encoder`` -- are skipped like
+multi_processing.py:35,65), then ``grad /= global num_steps`` and the same optimizer step on
+every rank, so the replicas stay bit-identical.  The stat scalars ride a second, ~200-byte
+float64 all-reduce so that step / episode counts stay exact.
+"""
+import numbers
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from .utils import merge_stat
+
+
+def _dist_on():
+    return dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+
+
+def flat_grad_buffer(params):
+    """One contiguous fp32 buffer holding every existing gradient (in parameter order)."""
+    gs = [p.grad for p in params if p.grad is not None]
+    if not gs:
+        return None, []
+    flat = torch.cat([g.reshape(-1) for g in gs])
+    return flat, gs
+
+
+def unflatten_into(flat, grads):
+    off = 0
+    for g in grads:
+        n = g.numel()
+        g.copy_(flat[off:off + n].view_as(g))
+        off += n
+
+
+def pack_stat(stat, device):
+    """Numbers and numpy arrays (merge_stat's additive kinds, utils.py:19-22) -> float64 vector."""
+    keys = sorted(k for k, v in stat.items() if isinstance(v, (numbers.Number, np.ndarray)))
+    parts, shapes = [], []
+    for k in keys:
+        v = np.atleast_1d(np.asarray(stat[k], dtype=np.float64))
+        shapes.append((k, v.shape, isinstance(stat[k], numbers.Number)))
+        parts.append(v.ravel())
+    vec = torch.from_numpy(np.concatenate(parts) if parts else np.zeros(0)).to(device)
+    return vec, shapes
+
+
+def unpack_stat(vec, shapes, stat):
+    v = vec.cpu().numpy()
+    off = 0
+    for k, shp, scalar in shapes:
+        n = int(np.prod(shp))
+        x = v[off:off + n].reshape(shp)
+        off += n
+        if scalar:
+            x = float(x[0])
+            stat[k] = int(round(x)) if abs(x - round(x)) < 1e-9 else x
+        else:
+            stat[k] = x
+    return stat
+
+
+class MultiGPUTrainer(object):
+    """Same surface as ``MultiProcessTrainer``: ``train_batch``, ``quit``, ``state_dict``,
+    ``load_state_dict`` (multi_processing.py:41-104)."""
+
+    def __init__(self, args, trainer_maker):
+        self.args = args
+        self.trainer = trainer_maker()
+        self.world = dist.get_world_size() if _dist_on() else 1
+        self.rank = dist.get_rank() if _dist_on() else 0
+        self.is_random = getattr(args, 'random', False)
+        self.collectives = 0          # gradient all-reduces issued (one per update)
+
+    def quit(self):
+        return
+
+    def reduce(self, stat):
+        """Sum gradients and additive stats over ranks; returns the merged stat."""
+        params = self.trainer.params
+        flat, grads = flat_grad_buffer(params)
+        dev = flat.device if flat is not None else (params[0].device if params else torch.device('cpu'))
+        vec, shapes = pack_stat(stat, dev)
+        if _dist_on():
+            if flat is not None:
+                dist.all_reduce(flat, op=dist.ReduceOp.SUM)      # multi_processing.py:92-94
+                self.collectives += 1
+            dist.all_reduce(vec, op=dist.ReduceOp.SUM)           # multi_processing.py:86-88
+        stat = unpack_stat(vec, shapes, dict(stat))
+        if flat is not None:
+            flat /= stat['num_steps']                            # multi_processing.py:95 (global step count)
+            unflatten_into(flat, grads)
+        return stat
+
+    def train_batch(self, epoch):
+        batch, stat = self.trainer.run_batch(epoch)
+        self.trainer.optimizer.zero_grad(set_to_none=False)
+        s = self.trainer.compute_grad(batch)
+        merge_stat(s, stat)
+        stat = self.reduce(stat)
+        self.trainer.optimizer.step()                            # multi_processing.py:97
+        return stat
+
+    def state_dict(self):
+        return self.trainer.state_dict()
+
+    def load_state_dict(self, state):
+        self.trainer.load_state_dict(state)
