@@ -423,16 +423,22 @@ def e2e_loop(a, env, net, steps, np, torch, select_action):
     env_act_h = pin(B, N, dtype=torch.int32)
     h2d = d2h = 0
 
+    phases = dict(policy_enqueue=0.0, wait_actions=0.0, env_enqueue=0.0, wait_reward=0.0)
+
     def one_step(obs, hc, info, count):
         nonlocal h2d, d2h
+        t0 = time.perf_counter()
         action_out, value, hc = net([obs, hc], info)                     # comm_action / alive_mask: host -> device
         action = select_action(a, action_out)
         act_h.copy_(action, non_blocking=True)                           # D2H (translate_action -> numpy)
+        t1 = time.perf_counter()
         torch.cuda.synchronize()
+        t2 = time.perf_counter()
         env_act_h.copy_(act_h[..., 0])
         obs, reward, done, info_env = env.step([env_act_h])              # H2D actions
         rew_h.copy_(reward, non_blocking=True)                           # D2H
         done_h.copy_(done, non_blocking=True)
+        t3 = time.perf_counter()
         nxt = {}
         if a.hard_attn:
             comm_h.copy_(act_h[..., -1] if not a.comm_action_one else torch.ones(B, N, dtype=torch.uint8))
@@ -442,6 +448,10 @@ def e2e_loop(a, env, net, steps, np, torch, select_action):
             nxt["alive_mask"] = alive_h
         torch.cuda.synchronize()
         if count:
+            t4 = time.perf_counter()
+            for k, v in zip(("policy_enqueue", "wait_actions", "env_enqueue", "wait_reward"),
+                            (t1 - t0, t2 - t1, t3 - t2, t4 - t3)):
+                phases[k] += v
             h2d += env_act_h.numel() * 4 + (comm_h.numel() if a.hard_attn else 0) + (alive_h.numel() if is_tj else 0)
             d2h += act_h.numel() * 4 + rew_h.numel() * 4 + done_h.numel() + (alive_h.numel() if is_tj else 0)
         if not is_tj and bool(done_h.any()):                             # finished PP envs start a new episode
@@ -468,6 +478,7 @@ def e2e_loop(a, env, net, steps, np, torch, select_action):
     e.err.zero_()
     return dict(value=B * N * steps / dt, unit="agent-env-steps/s", h2d_bytes_per_step=h2d // steps,
                 d2h_bytes_per_step=d2h // steps, steps=steps, ms_per_step=1e3 * dt / steps,
+                phases_ms={k: round(1e3 * v / steps, 4) for k, v in phases.items()},
                 api="CommNetMLP.forward -> select_action -> host actions -> GymWrapper.step -> host reward/done")
 
 

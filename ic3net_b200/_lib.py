@@ -101,6 +101,8 @@ SYMBOLS = {
     "ic3_policy_workspace_bytes": (C.c_uint64, [C.POINTER(PolicyCfg)]),
     "ic3_policy_step": (C.c_int, [C.POINTER(PolicyCfg), C.POINTER(PolicyPacked), C.POINTER(PolicyIO), _PTR]),
     "ic3_sample_actions": (C.c_int, [C.POINTER(PolicyCfg), _PTR, _PTR, _PTR, _PTR, _PTR]),
+    "ic3_returns_scan": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_float, C.c_float, _PTR, _PTR, _PTR, _PTR,
+                                   _PTR]),
 }
 
 _lib = None

@@ -1,18 +1,26 @@
-"""Batched GPU rollout behind the reference's ``trainer.Trainer`` surface (trainer.py:14-262).
+"""Batched GPU rollout + REINFORCE gradient behind the reference's ``trainer.Trainer`` surface
+(trainer.py:14-262).
 
 ``Trainer(args, policy_net, env)`` drives ``env.nenvs`` independent environment slots in
-lock-step on one GPU.  Each slot plays the role of one reference process: it runs
-episode after episode (auto-reset, hidden state zeroed, nobody talks at t = 0), and
-``run_batch`` returns once every slot has produced ``>= batch_size`` steps
-(``ceil(batch_size / max_steps) * max_steps`` lock-step iterations; an episode still
-open at the end of the batch is cut there, which is the only deviation from
-trainer.py:231-237, where the last episode may overshoot instead).
+lock-step on one GPU.  Each slot plays the role of one reference process: it runs episode after
+episode (auto-reset, hidden state zeroed, nobody talks at t = 0), and ``run_batch`` returns once
+every slot has produced ``>= batch_size`` steps (``ceil(batch_size / max_steps) * max_steps``
+lock-step iterations; an episode still open at the end of the batch is cut there, which is the
+only deviation from trainer.py:231-237, where the last episode may overshoot instead).
 
-One lock-step iteration is 3 kernel launches and no host synchronisation:
+Rollout (the hot path): one lock-step iteration is a handful of kernel launches and no host
+synchronisation:
   encoder (index form from the env state, or obs-gather + dense encoder)
-  -> policy step (comm mean, C, LSTM, heads, sampling)
+  -> policy step (comm mean, C, LSTM, heads, sampling; tcgen05 or fp32 SIMT kernels)
   -> env step + Trainer.get_episode bookkeeping + auto-reset (ic3_rollout_io).
 The whole T-step sequence can be captured once into a CUDA graph (``use_graph``).
+
+Gradient (``compute_grad``, trainer.py:128-225; scope row 8(f)-1): returns by a CUDA scan kernel,
+then the policy forward is RECOMPUTED with differentiable torch ops (fp32, batched over all slots)
+in windows of ``grad_window`` steps processed last-to-first; (h, c) at every window start are
+checkpointed during the rollout and the gradient w.r.t. them is handed to the previous window,
+so back-propagation through time is exact (truncated only where the reference truncates it:
+``detach_gap``, trainer.py:56-60, and episode starts).
 """
 import ctypes as C
 import math
@@ -20,6 +28,7 @@ from collections import namedtuple
 
 import numpy as np
 import torch
+import torch.nn.functional as F
 from torch import optim
 
 from . import _lib
@@ -44,9 +53,10 @@ class Trainer(object):
         self.obs_mode = getattr(args, 'obs_mode', 'index')      # 'index' | 'dense'
         self.use_graph = bool(getattr(args, 'use_graph', False))
         self.is_tj = args.env_name == 'traffic_junction'
+        self.record_for_grad = bool(getattr(args, 'record_for_grad', False))
+        self.grad_window = int(getattr(args, 'grad_window', 40))
         self._buf = None
         self._graph = None
-        self.launches_per_step = 3 if self.obs_mode == 'index' else 4
 
     # ------------------------------------------------------------------ buffers
     def _alloc(self, T):
@@ -65,10 +75,19 @@ class Trainer(object):
                  stat_reward=z(B, N), stat_comm=z(B, N), stat_success=z(B, dtype=torch.int32),
                  stat_episodes=z(B, dtype=torch.int32), stat_steps=z(B, dtype=torch.int32),
                  err=z(1, dtype=torch.int32))
-        if self.obs_mode == 'dense':
+        if self.obs_mode == 'dense' or (self.record_for_grad and self.is_tj):
             b['obs'] = torch.empty(B, N, self.env.observation_dim, dtype=torch.float32, device=dev)
-        if self.is_tj:
-            b['snap_obs'] = None
+        if self.record_for_grad:
+            # inputs of every policy step + (h, c) checkpoints at the window starts
+            W = self.grad_window
+            nw = (T + W - 1) // W
+            b.update(s_fresh=z(T, B, dtype=torch.uint8), s_comm=z(T, B, N, dtype=torch.uint8),
+                     s_alive=z(T, B, N, dtype=torch.uint8), s_tep=z(T, B, dtype=torch.int32),
+                     ck_h=z(nw, B * N, H), ck_c=z(nw, B * N, H))
+            if self.is_tj:
+                b['s_obs'] = z(T, B, N, self.env.observation_dim)
+            else:
+                b['s_loc'] = z(T, B, N + 1, 2, dtype=torch.int32)
         self._buf = b
         self._graph = None
         return b
@@ -86,13 +105,27 @@ class Trainer(object):
         hard = int(bool(args.hard_attn) and bool(args.commnet))
         s = _lib.stream()
         ws, _ = net.workspace(B)          # tensor-core path scratch (None for the fp32 SIMT kernel)
+        rec = self.record_for_grad
+        dense = self.obs_mode == 'dense' or (rec and self.is_tj)
         for t in range(T):
-            if self.obs_mode == 'dense':
+            if rec:
+                b['s_fresh'][t].copy_(b['fresh'])
+                b['s_comm'][t].copy_(b['comm'])
+                b['s_alive'][t].copy_(b['alive'])
+                b['s_tep'][t].copy_(b['t_ep'])
+                if not self.is_tj:
+                    b['s_loc'][t].copy_(e.loc)
+                if t % self.grad_window == 0:
+                    b['ck_h'][t // self.grad_window].copy_(b['h'])
+                    b['ck_c'][t // self.grad_window].copy_(b['c'])
+            if dense:
                 if self.is_tj:
                     _lib.check(lib.ic3_tj_obs(C.byref(e.cfg), C.byref(e.state), b['obs'].data_ptr(), s))
                 else:
                     _lib.check(lib.ic3_pp_obs(C.byref(e.cfg), C.byref(e.state), b['obs'].data_ptr(), s))
                 _lib.check(lib.ic3_encoder_dense(C.byref(cfg), C.byref(w), b['obs'].data_ptr(), b['x'].data_ptr(), s))
+                if rec and self.is_tj:
+                    b['s_obs'][t].copy_(b['obs'])
             elif self.is_tj:
                 _lib.check(lib.ic3_tj_encoder_index(C.byref(e.cfg), C.byref(e.state), C.byref(cfg), C.byref(w),
                                                     b['x'].data_ptr(), s))
@@ -122,33 +155,31 @@ class Trainer(object):
                 _lib.check(lib.ic3_pp_step(C.byref(e.cfg), C.byref(e.state), b['action'][t].data_ptr(), nh,
                                            b['step_reward'].data_ptr(), None, b['err'].data_ptr(), C.byref(r), s))
 
-    def rollout(self, T, epoch=0):
-        """T lock-step iterations from fresh episodes in every slot.  Returns (RolloutBatch, stat);
-        everything stays on the device except the small stat reductions."""
-        e = self.env.env
-        if self._buf is None or self._buf['T'] != T:
-            self._alloc(T)
-        b = self._buf
-        # episode boundary for every slot (trainer.py:28-32, 45-51)
+    def _episode_boundary(self, epoch):
+        e, b = self.env.env, self._buf
         if self.is_tj:
             e.reset(epoch, want_obs=False)
         else:
             e.reset(want_obs=False)
-        for k in ('stat_reward', 'stat_comm', 'stat_success', 'stat_episodes', 'stat_steps', 't_ep', 'err'):
+        for k in ('stat_reward', 'stat_comm', 'stat_success', 'stat_episodes', 'stat_steps', 't_ep'):
             b[k].zero_()
         b['fresh'].fill_(1)
-        self.policy_net.packed()                # (re)pack weights outside any graph capture
+
+    def rollout(self, T, epoch=0):
+        """T lock-step iterations from fresh episodes in every slot.  Returns a RolloutBatch of
+        stacked [T, B, ...] device tensors (views of the trainer's record buffers)."""
+        e = self.env.env
+        if self._buf is None or self._buf['T'] != T:
+            self._alloc(T)
+        b = self._buf
+        self._episode_boundary(epoch)             # trainer.py:28-32, 45-51
+        b['err'].zero_()
+        self.policy_net.packed()                  # (re)pack weights outside any graph capture
         if self.use_graph:
             if self._graph is None:
-                self._enqueue(T)                # warm-up (lazy function attributes, allocator)
+                self._enqueue(T)                  # warm-up (lazy function attributes, allocator)
                 torch.cuda.synchronize()
-                if self.is_tj:
-                    e.reset(epoch, want_obs=False)
-                else:
-                    e.reset(want_obs=False)
-                for k in ('stat_reward', 'stat_comm', 'stat_success', 'stat_episodes', 'stat_steps', 't_ep'):
-                    b[k].zero_()
-                b['fresh'].fill_(1)
+                self._episode_boundary(epoch)
                 g = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(g):
                     self._enqueue(T)
@@ -158,17 +189,17 @@ class Trainer(object):
                 self._graph.replay()
         else:
             self._enqueue(T)
-        batch = RolloutBatch(action=b['action'], logp=b['logp'], value=b['value'].view(T, e.nenvs, -1),
-                             reward=b['reward'], episode_mask=b['emask'], episode_mini_mask=b['mini'],
-                             alive_mask=b['ralive'], snapshot=None)
-        return batch
+        return RolloutBatch(action=b['action'], logp=b['logp'], value=b['value'].view(T, e.nenvs, -1),
+                            reward=b['reward'], episode_mask=b['emask'], episode_mini_mask=b['mini'],
+                            alive_mask=b['ralive'], snapshot=None)
 
     def collect_stat(self):
         """Host-side stat dict with the reference's keys (trainer.py:73-75,86-88,109-110,124-125),
         summed over the env slots of this GPU."""
         b, e, args = self._buf, self.env.env, self.args
-        if int(b['err'].item()):
-            raise RuntimeError("device-side error flag %d during rollout" % int(b['err'].item()))
+        flags = int(b['err'].item())
+        if flags:
+            raise RuntimeError("device-side error flag %#x during rollout" % flags)
         stat = dict()
         stat['num_episodes'] = int(b['stat_episodes'].sum().item())
         stat['num_steps'] = int(b['stat_steps'].sum().item())
@@ -196,12 +227,123 @@ class Trainer(object):
         self.stats = self.collect_stat()
         return batch, self.stats
 
-    def compute_grad(self, batch):
-        raise NotImplementedError("REINFORCE gradient (trainer.py:128-225) is the next row of the scope table")
+    # ------------------------------------------------------------------ gradient (trainer.py:128-225)
+    def _pp_sparse_obs(self, loc):
+        """Non-zeros of the PP observation (predator_prey_env.py:188-210) as (index, value) pairs
+        [R, 3*W*W] from a state snapshot loc [B, N+1, 2]."""
+        e = self.env.env
+        D, v, N = e.dim, e.vision, e.npredator
+        W, V = 2 * v + 1, e.vocab_size
+        loc = loc.long()
+        pr, pc = loc[:, :N, 0], loc[:, :N, 1]
+        ar = torch.arange(W, device=loc.device)
+        dy, dx = ar.repeat_interleave(W), ar.repeat(W)                       # window cell w = dy*W + dx
+        rr = pr.unsqueeze(-1) - v + dy                                       # [B, N, W*W]
+        cc = pc.unsqueeze(-1) - v + dx
+        inside = (rr >= 0) & (rr < D) & (cc >= 0) & (cc < D)
+        base = torch.arange(W * W, device=loc.device) * V
+        cls = torch.where(inside, rr * D + cc, torch.full_like(rr, D * D + 1)) + base
+        npred = ((rr.unsqueeze(-1) == pr[:, None, None, :]) & (cc.unsqueeze(-1) == pc[:, None, None, :])).sum(-1)
+        nprey = (rr == loc[:, N:, 0].unsqueeze(-1)) & (cc == loc[:, N:, 1].unsqueeze(-1))
+        idx = torch.cat([cls, (base + V - 2).expand_as(cls), (base + V - 1).expand_as(cls)], -1)
+        val = torch.cat([torch.ones_like(cls), nprey.long() * inside, npred * inside], -1).float()
+        return idx.reshape(-1, 3 * W * W), val.reshape(-1, 3 * W * W)
 
+    def _forward_window(self, t0, t1, h, c, adv, ret):
+        """Differentiable re-run of steps [t0, t1) for all slots; returns (loss, h, c, stats)."""
+        b, net, args = self._buf, self.policy_net, self.args
+        B, N, H = self.env.env.nenvs, args.nagents, args.hid_size
+        hard = bool(args.hard_attn) and bool(args.commnet)
+        comm_avg = getattr(args, 'comm_mode', 'avg') == 'avg'
+        w_e, b_e = net.encoder.weight, net.encoder.bias
+        w_eT = None if self.is_tj else w_e.t().contiguous()
+        loss = torch.zeros((), device=h.device)
+        st = dict(action_loss=torch.zeros((), device=h.device), value_loss=torch.zeros((), device=h.device),
+                  entropy=torch.zeros((), device=h.device))
+        for t in range(t0, t1):
+            keep = (1 - b['s_fresh'][t].float()).repeat_interleave(N).unsqueeze(1)        # trainer.py:50-51
+            h, c = h * keep, c * keep
+            if self.is_tj:
+                x = F.linear(b['s_obs'][t].reshape(B * N, -1), w_e, b_e)                  # comm.py:119
+            else:
+                idx, val = self._pp_sparse_obs(b['s_loc'][t])
+                x = F.embedding_bag(idx, w_eT, per_sample_weights=val, mode='sum') + b_e
+            fresh = b['s_fresh'][t].bool().unsqueeze(1)
+            alive = torch.where(fresh, torch.ones_like(b['s_alive'][t]), b['s_alive'][t]).float()   # comm.py:99-112
+            n_alive = alive.sum(1, keepdim=True)
+            g = alive
+            if hard:
+                g = g * torch.where(fresh, torch.zeros_like(b['s_comm'][t]), b['s_comm'][t]).float()  # :171-175
+            if args.comm_mask_zero:
+                S = torch.zeros_like(h)
+            else:
+                hv = h.view(B, N, H)
+                gg = g.unsqueeze(-1)
+                tot = (gg * hv).sum(1, keepdim=True)
+                den = torch.where(n_alive > 1, n_alive - 1, torch.ones_like(n_alive)) if comm_avg \
+                    else torch.ones_like(n_alive)
+                S = (gg * (tot - gg * hv) / den.unsqueeze(-1)).reshape(B * N, H)           # comm.py:181-205
+            inp = x + net.C_modules[0](S)                                                  # comm.py:206,211
+            h, c = net.f_module(inp, (h, c))                                               # comm.py:213-218
+            value = net.value_head(h).view(B, N)
+            alive_post = b['ralive'][t].float()
+            act = b['action'][t].long()
+            lp_taken = torch.zeros(B, N, device=h.device)
+            ent = torch.zeros((), device=h.device)
+            for k, head in enumerate(net.heads):
+                lp = F.log_softmax(head(h), dim=-1).view(B, N, -1)                         # comm.py:239
+                lp_taken = lp_taken + lp.gather(-1, act[..., k:k + 1]).squeeze(-1)         # utils.py:42-46
+                ent = ent - (lp * lp.exp()).sum()
+            a_loss = (-adv[t] * lp_taken * alive_post).sum()                               # trainer.py:198-201
+            v_loss = ((value - ret[t]).pow(2) * alive_post).sum()                          # :205-208
+            step_loss = a_loss + args.value_coeff * v_loss
+            if args.entr > 0:
+                step_loss = step_loss - args.entr * ent                                    # :211-220
+            loss = loss + step_loss
+            st['action_loss'] += a_loss.detach(); st['value_loss'] += v_loss.detach(); st['entropy'] += ent.detach()
+            det = (((b['s_tep'][t] + 1) % args.detach_gap) == 0).repeat_interleave(N).unsqueeze(1)   # trainer.py:56-60
+            if bool(args.detach_gap <= self.args.max_steps):
+                h = torch.where(det, h.detach(), h)
+                c = torch.where(det, c.detach(), c)
+        return loss, h, c, st
+
+    def compute_grad(self, batch):
+        """REINFORCE + value + entropy loss summed over every slot and step of the batch, gradients
+        accumulated into ``p.grad`` (not yet divided by num_steps: train_batch does that,
+        trainer.py:251-253).  Needs ``args.record_for_grad`` during the rollout."""
+        if not self.record_for_grad:
+            raise RuntimeError("set args.record_for_grad = True before the rollout to use compute_grad")
+        b, args = self._buf, self.args
+        e = self.env.env
+        T, B, N = b['T'], e.nenvs, args.nagents
+        ret = torch.empty(T, B, N, device=e.device)
+        _lib.check(_lib.load().ic3_returns_scan(T, B, N, float(args.gamma), float(args.mean_ratio),
+                                                b['reward'].data_ptr(), b['emask'].data_ptr(), b['mini'].data_ptr(),
+                                                ret.data_ptr(), _lib.stream()))
+        adv = ret - b['value'].view(T, B, N)                                               # trainer.py:176-177
+        if args.normalize_rewards:                                                         # :179-180, per slot
+            adv = (adv - adv.mean((0, 2), keepdim=True)) / adv.std((0, 2), keepdim=True)
+        W = self.grad_window
+        nw = (T + W - 1) // W
+        dh = dc = None
+        tot = dict(action_loss=0.0, value_loss=0.0, entropy=0.0)
+        for k in reversed(range(nw)):
+            t0, t1 = k * W, min(T, (k + 1) * W)
+            h0 = b['ck_h'][k].clone().requires_grad_(True)
+            c0 = b['ck_c'][k].clone().requires_grad_(True)
+            loss, h1, c1, st = self._forward_window(t0, t1, h0, c0, adv, ret)
+            if dh is not None:                     # gradient arriving from the later window
+                loss = loss + (h1 * dh).sum() + (c1 * dc).sum()
+            loss.backward()
+            dh, dc = h0.grad.detach(), c0.grad.detach()
+            for key in tot:
+                tot[key] += float(st[key].item())
+        return tot
+
+    # only used when there is a single process (trainer.py:245-256)
     def train_batch(self, epoch):
         batch, stat = self.run_batch(epoch)
-        self.optimizer.zero_grad()
+        self.optimizer.zero_grad(set_to_none=False)
         s = self.compute_grad(batch)
         merge_stat(s, stat)
         for p in self.params:

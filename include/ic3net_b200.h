@@ -261,6 +261,13 @@ int ic3_policy_step(const ic3_policy_cfg* cfg, const ic3_policy_packed* w, const
 int ic3_sample_actions(const ic3_policy_cfg* cfg, const float* logp, const uint32_t* tick,
                        const uint32_t* draws, int32_t* action, void* stream);
 
+/* ------------------------------------------------------------------------
+ * REINFORCE returns  (trainer.py:160-173), the first step of Trainer.compute_grad
+ * ---------------------------------------------------------------------- */
+/* reward, mini_mask: [T,B,N]; episode_mask: [T,B]; returns out: [T,B,N] float32 (float64 accumulation). */
+int ic3_returns_scan(int32_t T, int32_t B, int32_t N, float gamma, float mean_ratio, const float* reward,
+                     const uint8_t* episode_mask, const uint8_t* mini_mask, float* returns, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

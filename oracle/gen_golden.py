@@ -458,6 +458,86 @@ def gen_episode_case(name, seed, env_ids, wseed, hsteps=(0, 1), epoch=0, **kw):
     save(name, meta, **arrays)
 
 
+# --------------------------------------------------------------------------
+# 5. REINFORCE gradient of a whole batch through the reference's Trainer.run_batch + compute_grad
+# --------------------------------------------------------------------------
+def gen_grad_case(name, seed, env_id, wseed, **kw):
+    import torch
+    from . import grad as ograd
+    from .rollout import run_episode
+    torch.set_default_dtype(torch.float64)
+    ref_shims.install()
+    from comm import CommNetMLP
+    from trainer import Trainer
+    args = ref_shims.make_args(**kw)
+    w = ref_shims.make_ref_env(args)
+    ref_shims.finish_args(args, w)
+    heads = args.naction_heads
+    net = CommNetMLP(args, args.num_inputs)
+    sd = make_weights(wseed, args.num_inputs, args.hid_size, heads, args.comm_init)
+    net.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()})
+    tr = Trainer(args, net, w)
+    is_tj = args.env_name == "traffic_junction"
+    tables = tj_tables_from_ref(w.env) if is_tj else None
+    rr = RefRandom(seed, env_id)
+    orig_step, orig_reset = w.step, w.reset
+
+    def step(action, _o=orig_step):
+        rr.group = -1
+        out = _o(action)
+        rr.tick += 1
+        rr.head = 0
+        return out
+
+    def reset(epoch, _o=orig_reset):
+        out = _o(epoch)
+        rr.episode += 1
+        return out
+    w.step, w.reset = step, reset
+    with routed(rr):
+        batch, stat = tr.run_batch(0)
+    w.step, w.reset = orig_step, orig_reset
+    tr.optimizer.zero_grad()
+    s = tr.compute_grad(batch)
+    ref_grads = {k: (v.grad.numpy().copy() if v.grad is not None else None) for k, v in net.named_parameters()}
+    # ---- oracle replay ----
+    params = policy.params_to_f64(sd)
+    orc = make_oracle_env(args, tables)
+    eps, tick, k = [], 0, 0
+    while tick < stat["num_steps"]:
+        ep = run_episode(orc, params, args, seed, env_id, epoch=0, tick0=tick, episode=k)
+        eps.append(ep)
+        tick += ep["num_steps"]
+        k += 1
+    assert tick == stat["num_steps"] and k == stat["num_episodes"]
+    g, ostat, extra = ograd.compute_grad(params, eps, args)
+    assert np.isclose(ostat["action_loss"], s["action_loss"], rtol=1e-9, atol=1e-9), (ostat, s)
+    assert np.isclose(ostat["value_loss"], s["value_loss"], rtol=1e-9, atol=1e-9)
+    assert np.isclose(ostat["entropy"], s["entropy"], rtol=1e-9, atol=1e-9)
+    arrays = {}
+    for key, rg in ref_grads.items():
+        if rg is None:
+            assert g[key] is None or not np.any(g[key]), key
+            continue
+        scale = max(1.0, float(np.abs(rg).max()))
+        assert np.allclose(g[key], rg, rtol=1e-8, atol=1e-9 * scale), (name, key, np.abs(g[key] - rg).max())
+        if rg.size <= 4096:
+            arrays["g_" + key] = rg
+        else:
+            arrays["gsum_" + key] = np.array([rg.sum(), np.abs(rg).sum(), (rg ** 2).sum()])
+            arrays["gsample_" + key] = rg.ravel()[::max(1, rg.size // 2048)][:2048].copy()
+    meta = dict(kind="grad", seed=seed, env_id=env_id, weights_seed=wseed,
+                args={k_: v for k_, v in vars(args).items() if isinstance(v, (int, float, str, bool))},
+                obs_dim=int(args.num_inputs), heads=list(map(int, heads)), num_steps=int(stat["num_steps"]),
+                num_episodes=int(stat["num_episodes"]), action_loss=float(s["action_loss"]),
+                value_loss=float(s["value_loss"]), entropy=float(s["entropy"]))
+    arrays["returns"] = extra["returns"]
+    if is_tj:
+        arrays["grid"] = tables["grid"]
+        arrays["route_len"], arrays["route_cells"] = pack_routes(tables["routes"])
+    save(name, meta, **arrays)
+
+
 def main():
     if not ref_shims.reference_available():
         print("reference not available; nothing generated")
@@ -508,6 +588,17 @@ def main():
     gen_episode_case("ep_tj_medium_v1_commnet", 47, (1,), 57, hsteps=(0, 1, 20), env_name="traffic_junction",
                      nagents=10, dim=14, vision=1, max_steps=40, hid_size=64, commnet=True, difficulty="medium",
                      add_rate_min=0.2, add_rate_max=0.2)
+    gen_grad_case("grad_pp_easy_ic3net", 61, 2, 71, env_name="predator_prey", nagents=3, dim=5, vision=0,
+                  max_steps=20, hid_size=128, ic3net=True, batch_size=50, detach_gap=10, value_coeff=0.01)
+    gen_grad_case("grad_pp_coop_commnet_entr", 62, 1, 72, env_name="predator_prey", nagents=4, dim=3, vision=1,
+                  max_steps=12, hid_size=32, commnet=True, batch_size=40, mode="cooperative", entr=0.01,
+                  mean_ratio=1.0, gamma=0.95, normalize_rewards=True)
+    gen_grad_case("grad_tj_medium_ic3net", 63, 4, 73, env_name="traffic_junction", nagents=10, dim=14, vision=0,
+                  max_steps=40, hid_size=128, ic3net=True, difficulty="medium", add_rate_min=0.2, add_rate_max=0.2,
+                  batch_size=70, detach_gap=10)
+    gen_grad_case("grad_tj_easy_commnet", 64, 0, 74, env_name="traffic_junction", nagents=5, dim=6, vision=0,
+                  max_steps=20, hid_size=64, commnet=True, difficulty="easy", add_rate_min=0.3, add_rate_max=0.3,
+                  batch_size=50, mean_ratio=0.5, gamma=0.9)
     return 0
 
 

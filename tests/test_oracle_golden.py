@@ -135,3 +135,40 @@ def test_episode_golden(name):
             assert np.allclose(ep["h"][t], g("h_sel")[j], rtol=1e-12, atol=1e-13)
             assert np.allclose(ep["c"][t], g("c_sel")[j], rtol=1e-12, atol=1e-13)
         assert ep["success"] == int(g("success"))
+
+
+@pytest.mark.parametrize("name", golden_names("grad_"))
+def test_gradient_golden(name):
+    """oracle/grad.py against the gradients of the reference's own Trainer.compute_grad."""
+    from oracle import grad as ograd
+    from oracle.rollout import run_episode
+    meta, z = load_golden(name)
+    args = ns(meta["args"])
+    is_tj = args.env_name == "traffic_junction"
+    sd = make_weights(meta["weights_seed"], meta["obs_dim"], args.hid_size, meta["heads"], args.comm_init)
+    p = policy.params_to_f64(sd)
+    env = make_oracle_env(args, tj_tables(z) if is_tj else None)
+    eps, tick, k = [], 0, 0
+    while tick < meta["num_steps"]:
+        ep = run_episode(env, p, args, meta["seed"], meta["env_id"], epoch=0, tick0=tick, episode=k)
+        eps.append(ep)
+        tick += ep["num_steps"]
+        k += 1
+    assert k == meta["num_episodes"]
+    g, st, extra = ograd.compute_grad(p, eps, args)
+    assert np.isclose(st["action_loss"], meta["action_loss"], rtol=1e-9, atol=1e-9)
+    assert np.isclose(st["value_loss"], meta["value_loss"], rtol=1e-9, atol=1e-9)
+    assert np.isclose(st["entropy"], meta["entropy"], rtol=1e-9, atol=1e-9)
+    assert np.allclose(extra["returns"], z["returns"], rtol=1e-12, atol=1e-12)
+    checked = 0
+    for key in z.files:
+        if key.startswith("g_"):
+            assert np.allclose(g[key[2:]], z[key], rtol=1e-8, atol=1e-10), key
+            checked += 1
+        elif key.startswith("gsample_"):
+            q = g[key[8:]]
+            assert np.allclose(q.ravel()[::max(1, q.size // 2048)][:2048], z[key], rtol=1e-8, atol=1e-10), key
+            ref = z["gsum_" + key[8:]]
+            assert np.allclose([q.sum(), np.abs(q).sum(), (q ** 2).sum()], ref, rtol=1e-8)
+            checked += 1
+    assert checked >= 8
