@@ -317,7 +317,7 @@ def gpu_arm(opts):
             del tr2, net2, env2
 
         # ---- e2e: the public, reference-shaped API with host-side actions / rewards ----
-        e2e = None if opts.quick else e2e_loop(a, env, net, min(K, 40), np, torch, select_action)
+        e2e = None if opts.quick else e2e_loop(a, env, net, min(K, 200), np, torch, select_action)
 
         # ---- CPU baseline (bounded sample of the same workload on the host cores) ----
         cores = host_cores()
@@ -470,15 +470,29 @@ def e2e_loop(a, env, net, steps, np, torch, select_action):
     for _ in range(3):
         obs, hc, info = one_step(obs, hc, info, False)
     torch.cuda.synchronize()
+    import gc
+    gc.collect()
+    gc.freeze()          # keep the generational GC from walking the whole (torch-sized) heap inside the timed loop
+    ms0 = torch.cuda.memory_stats()
     t0 = time.perf_counter()
+    per_step = []
     for _ in range(steps):
+        ts = time.perf_counter()
         obs, hc, info = one_step(obs, hc, info, True)
+        per_step.append(time.perf_counter() - ts)
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
+    gc.unfreeze()
+    per_step.sort()
+    ms1 = torch.cuda.memory_stats()
     e.err.zero_()
     return dict(value=B * N * steps / dt, unit="agent-env-steps/s", h2d_bytes_per_step=h2d // steps,
                 d2h_bytes_per_step=d2h // steps, steps=steps, ms_per_step=1e3 * dt / steps,
                 phases_ms={k: round(1e3 * v / steps, 4) for k, v in phases.items()},
+                step_ms_median=round(1e3 * per_step[len(per_step) // 2], 4), step_ms_max=round(1e3 * per_step[-1], 4),
+                step_ms_sorted_tail=[round(1e3 * x, 3) for x in per_step[-4:]],
+                cuda_mallocs_in_loop=int(ms1.get("num_device_alloc", 0) - ms0.get("num_device_alloc", 0)),
+                cuda_frees_in_loop=int(ms1.get("num_device_free", 0) - ms0.get("num_device_free", 0)),
                 api="CommNetMLP.forward -> select_action -> host actions -> GymWrapper.step -> host reward/done")
 
 
