@@ -195,6 +195,10 @@ def gpu_arm(opts):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    # Host-side work is a few tiny tensor ops per step; letting torch fan them out over every visible
+    # core (128 here, with a 16-core cgroup quota) only earns CPU throttling stalls.  The reference's
+    # README asks for OMP_NUM_THREADS=1 as well (README.md:48); torchrun sets the same default.
+    torch.set_num_threads(1)
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
