@@ -110,6 +110,7 @@ def main(argv=None):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.set_num_threads(1)                         # README.md:48 (OMP_NUM_THREADS=1); host work is tiny
     torch.cuda.set_device(local)
     if world > 1:
         torch.distributed.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -135,6 +136,7 @@ def main(argv=None):
     if rank == 0:
         print(args)
 
+    args.record_for_grad = not args.rollout_only     # keep the inputs compute_grad re-runs (trainer.py)
     policy_net = CommNetMLP(args, num_inputs)
     trainer = MultiGPUTrainer(args, lambda: Trainer(args, policy_net, env))
 
