@@ -280,16 +280,28 @@ __device__ __forceinline__ float tanh_fast(float v) {
 //                      overlaps the MMAs of item i+1
 // Work item = (128-row tile, 256-column half); item 2t and 2t+1 share the A tile (second read hits L2).
 constexpr int NSTAGE_P = 4;
+constexpr int HEAD_PAD = 8;          // outputs (value + action logits) the fused epilogue supports
 constexpr int TC_P_THREADS = 320;
 constexpr int EPI_THREADS = 256;
 
 __global__ void __launch_bounds__(TC_P_THREADS, 1) lstm_tc_kernel(ic3_policy_cfg cfg, ic3_policy_io io,
                                                                  const __half* __restrict__ a_img,
                                                                  const __half* __restrict__ b_img,
-                                                                 const float* __restrict__ bias_cat, int nitems) {
+                                                                 const float* __restrict__ bias_cat, int nitems,
+                                                                 const float* __restrict__ head_w, int nout,
+                                                                 float* __restrict__ partial) {
   extern __shared__ __align__(1024) unsigned char smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + NSTAGE_P * STAGE_BYTES);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
+  // head weights, unit-major [128][8] (zero padded): the epilogue folds value/action-head dot products
+  // of its 32 hidden units into per-slot partial logits (partial != nullptr  <=>  nout <= 8)
+  float* s_hw = reinterpret_cast<float*>(smem + NSTAGE_P * STAGE_BYTES + 256);
+  if (partial) {
+    for (int idx = threadIdx.x; idx < TC_H * HEAD_PAD; idx += blockDim.x) {
+      const int u = idx / HEAD_PAD, o = idx - u * HEAD_PAD;
+      s_hw[idx] = o < nout ? __ldg(head_w + (size_t)o * TC_H + u) : 0.f;
+    }
+  }
   const uint32_t bar_full = smem_u32(bars), bar_empty = smem_u32(bars + NSTAGE_P);
   const uint32_t bar_tfull = smem_u32(bars + 2 * NSTAGE_P), bar_tempty = smem_u32(bars + 2 * NSTAGE_P + 2);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -380,6 +392,9 @@ __global__ void __launch_bounds__(TC_P_THREADS, 1) lstm_tc_kernel(ic3_policy_cfg
       bool fr = false;
       if (valid && io.fresh) fr = io.fresh[row / cfg.N] != 0;
       const uint32_t taddr = tmem_base + acc * TC_NH + chalf * 128 + ((uint32_t)(quarter * 32) << 16);
+      float part[HEAD_PAD];
+#pragma unroll
+      for (int o = 0; o < HEAD_PAD; ++o) part[o] = 0.f;
 #pragma unroll 2
       for (int cg = 0; cg < 8; ++cg) {
         uint32_t v[16];
@@ -402,10 +417,26 @@ __global__ void __launch_bounds__(TC_P_THREADS, 1) lstm_tc_kernel(ic3_policy_cfg
           }
           *reinterpret_cast<float4*>(io.c_out + (size_t)row * TC_H + u0) = make_float4(cn[0], cn[1], cn[2], cn[3]);
           *reinterpret_cast<float4*>(io.h_out + (size_t)row * TC_H + u0) = make_float4(hn[0], hn[1], hn[2], hn[3]);
+          if (partial) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float4 w0 = *reinterpret_cast<const float4*>(&s_hw[(u0 + j) * HEAD_PAD]);
+              const float4 w1 = *reinterpret_cast<const float4*>(&s_hw[(u0 + j) * HEAD_PAD + 4]);
+              part[0] = fmaf(hn[j], w0.x, part[0]); part[1] = fmaf(hn[j], w0.y, part[1]);
+              part[2] = fmaf(hn[j], w0.z, part[2]); part[3] = fmaf(hn[j], w0.w, part[3]);
+              part[4] = fmaf(hn[j], w1.x, part[4]); part[5] = fmaf(hn[j], w1.y, part[5]);
+              part[6] = fmaf(hn[j], w1.z, part[6]); part[7] = fmaf(hn[j], w1.w, part[7]);
+            }
+          }
         }
       }
       tc_fence_before();
       mbar_arrive(bar_tempty + 8 * acc);   // this thread no longer reads the accumulator
+      if (partial && valid) {              // slot = (column half of the CTA item, column half of the warp)
+        float4* dst = reinterpret_cast<float4*>(partial + ((size_t)row * 4 + (nh * 2 + chalf)) * HEAD_PAD);
+        dst[0] = make_float4(part[0], part[1], part[2], part[3]);
+        dst[1] = make_float4(part[4], part[5], part[6], part[7]);
+      }
     }
   }
   tc_fence_before();
@@ -495,13 +526,78 @@ __global__ void __launch_bounds__(256) heads_kernel(ic3_policy_cfg cfg, ic3_poli
   }
 }
 
+// Finish the heads from the four per-slot partial logits (fixed summation order -> deterministic):
+// value, log-softmax per head, inverse-CDF sampling.  One thread per agent row.
+__global__ void __launch_bounds__(128) heads_finish_kernel(ic3_policy_cfg cfg, ic3_policy_packed w, ic3_policy_io io,
+                                                            const float* __restrict__ partial) {
+  const long row = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= (long)cfg.B * cfg.N) return;
+  float logit[HEAD_PAD];
+  const float4* p4 = reinterpret_cast<const float4*>(partial + (size_t)row * 4 * HEAD_PAD);
+  {
+    float4 a = p4[0], b = p4[1];
+#pragma unroll
+    for (int sl = 1; sl < 4; ++sl) {
+      const float4 c = p4[2 * sl], d = p4[2 * sl + 1];
+      a.x += c.x; a.y += c.y; a.z += c.z; a.w += c.w;
+      b.x += d.x; b.y += d.y; b.z += d.z; b.w += d.w;
+    }
+    logit[0] = a.x; logit[1] = a.y; logit[2] = a.z; logit[3] = a.w;
+    logit[4] = b.x; logit[5] = b.y; logit[6] = b.z; logit[7] = b.w;
+  }
+  int atot = 0;
+  for (int k = 0; k < cfg.nheads; ++k) atot += cfg.head_dim[k];
+#pragma unroll
+  for (int o = 0; o < HEAD_PAD; ++o) logit[o] += (o < 1 + atot) ? __ldg(w.head_b + o) : 0.f;
+  io.value[row] = logit[0];
+  const int e = (int)(row / cfg.N), i = (int)(row - (long)e * cfg.N);
+  const bool do_sample = io.action != nullptr;
+  uint4 d24 = make_uint4(0, 0, 0, 0);
+  if (do_sample && !io.draws)
+    d24 = ic3_draw24(cfg.seed, cfg.env_id0 + (uint32_t)e, io.tick ? io.tick[e] : 0u, IC3_STREAM_ACTION, (uint32_t)i);
+  int off = 1;
+  for (int k = 0; k < cfg.nheads; ++k) {
+    const int na = cfg.head_dim[k];
+    float m = -INFINITY;
+#pragma unroll
+    for (int o = 1; o < HEAD_PAD; ++o)
+      if (o >= off && o < off + na) m = fmaxf(m, logit[o]);
+    float ssum = 0.f;
+#pragma unroll
+    for (int o = 1; o < HEAD_PAD; ++o)
+      if (o >= off && o < off + na) ssum += expf(logit[o] - m);
+    const float lse = m + logf(ssum);
+    uint32_t u24 = 0;
+    if (do_sample) u24 = io.draws ? io.draws[(size_t)row * cfg.nheads + k] : ic3_word(d24, k);
+    const float u = (float)u24 * 5.9604644775390625e-08f;
+    float cdf = 0.f;
+    int act = na - 1;
+    bool found = false;
+#pragma unroll
+    for (int o = 1; o < HEAD_PAD; ++o) {
+      if (o >= off && o < off + na) {
+        const float lp = logit[o] - lse;
+        io.logp[(size_t)row * atot + (o - 1)] = lp;
+        cdf += expf(lp);
+        if (!found && cdf > u) {
+          act = o - off;
+          found = true;
+        }
+      }
+    }
+    if (do_sample) io.action[(size_t)row * cfg.nheads + k] = act;
+    off += na;
+  }
+}
+
 }  // namespace
 
 uint64_t ic3_tc_workspace_bytes(const ic3_policy_cfg* cfg) {
   if (!cfg || cfg->H != TC_H) return 0;
   const long R = (long)cfg->B * cfg->N;
   const long ntiles = (R + TC_M - 1) / TC_M;
-  return (uint64_t)ntiles * TC_NCHUNK * A_CHUNK_BYTES;
+  // operand image + per-slot partial logits [R][4][HEAD_PAD]
+  return (uint64_t)ntiles * TC_NCHUNK * A_CHUNK_BYTES + (uint64_t)R * 4 * HEAD_PAD * sizeof(float);
 }
 
 int ic3_tc_pack(const ic3_policy_cfg* cfg, const ic3_policy_params* p, const ic3_policy_packed* out, cudaStream_t s) {
@@ -520,7 +616,13 @@ int ic3_tc_policy_step(const ic3_policy_cfg* cfg, const ic3_policy_packed* w, co
   __half* img = reinterpret_cast<__half*>(io->workspace);
   prep_kernel<<<2 * ntiles, 256, 0, s>>>(*cfg, *io, img);
   IC3_LAUNCH_CHECK();
-  const size_t smem = NSTAGE_P * STAGE_BYTES + 256;
+  const size_t smem = NSTAGE_P * STAGE_BYTES + 256 + TC_H * HEAD_PAD * sizeof(float);
+  int nout = 1;
+  for (int k = 0; k < cfg->nheads; ++k) nout += cfg->head_dim[k];
+  const bool fused_heads = nout <= HEAD_PAD;
+  float* partial = fused_heads ? reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(io->workspace) +
+                                                           (size_t)ntiles * TC_NCHUNK * A_CHUNK_BYTES)
+                               : nullptr;
   static int num_sms = 0;
   if (num_sms == 0) {
     cudaError_t e = cudaFuncSetAttribute(lstm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -533,10 +635,13 @@ int ic3_tc_policy_step(const ic3_policy_cfg* cfg, const ic3_policy_packed* w, co
   const int nitems = 2 * ntiles;
   const int grid = nitems < num_sms ? nitems : num_sms;
   lstm_tc_kernel<<<grid, TC_P_THREADS, smem, s>>>(*cfg, *io, img, reinterpret_cast<const __half*>(w->lstm_img),
-                                                   w->bias_cat, nitems);
+                                                   w->bias_cat, nitems, w->head_w, nout, partial);
   IC3_LAUNCH_CHECK();
-  int nout = 1;
-  for (int k = 0; k < cfg->nheads; ++k) nout += cfg->head_dim[k];
+  if (fused_heads) {
+    heads_finish_kernel<<<(int)((R + 127) / 128), 128, 0, s>>>(*cfg, *w, *io, partial);
+    IC3_LAUNCH_CHECK();
+    return IC3_OK;
+  }
   const int P = nout <= 8 ? 8 : (nout <= 16 ? 16 : 32);
   const long rows_per_block = 8L * (32 / P);
   const int hgrid = (int)((R + rows_per_block - 1) / rows_per_block);
