@@ -272,17 +272,19 @@ __device__ __forceinline__ float tanh_fast(float v) {
 
 // ---- the tensor-core kernel -----------------------------------------------------------------------
 // Persistent, one CTA per SM, warp-specialised:
-//   warp 8  producer   ring of NSTAGE (A 16 KB + B 32 KB) stages filled by cp.async.bulk, running
+//   warp 16 producer   ring of NSTAGE (A 16 KB + B 32 KB) stages filled by cp.async.bulk, running
 //                      ahead across work items
-//   warp 9  MMA        one thread issues 3 x tcgen05.mma (128 x 256 x 16) per k-step into one of
+//   warp 17 MMA        one thread issues 3 x tcgen05.mma (128 x 256 x 16) per k-step into one of
 //                      two 256-column TMEM accumulators
-//   warps 0-7 epilogue warp w owns TMEM lanes 32*(w%4).. and columns 128*(w/4)..: LSTM cell of item i
+//   warps 0-15 epilogue warp w owns TMEM lanes 32*(w%4).. and columns 64*(w/4)..: LSTM cell of item i
 //                      overlaps the MMAs of item i+1
 // Work item = (128-row tile, 256-column half); item 2t and 2t+1 share the A tile (second read hits L2).
 constexpr int NSTAGE_P = 4;
 constexpr int HEAD_PAD = 8;          // outputs (value + action logits) the fused epilogue supports
-constexpr int TC_P_THREADS = 320;
-constexpr int EPI_THREADS = 256;
+constexpr int EPI_WARPS = 16;        // 4 warps per TMEM lane quarter, 64 accumulator columns (16 hidden units) each
+constexpr int EPI_THREADS = EPI_WARPS * 32;
+constexpr int TC_P_THREADS = EPI_THREADS + 64;   // + producer warp + MMA warp
+constexpr int NSLOT = 8;             // partial-logit slots per row: (column half of the item) x (column quarter of the warp)
 
 __global__ void __launch_bounds__(TC_P_THREADS, 1) lstm_tc_kernel(ic3_policy_cfg cfg, ic3_policy_io io,
                                                                  const __half* __restrict__ a_img,
@@ -317,7 +319,7 @@ __global__ void __launch_bounds__(TC_P_THREADS, 1) lstm_tc_kernel(ic3_policy_cfg
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 8) {   // all 512 TMEM columns: two 128-lane x 256-column fp32 accumulators
+  if (warp == EPI_WARPS) {   // all 512 TMEM columns: two 128-lane x 256-column fp32 accumulators
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -327,7 +329,7 @@ __global__ void __launch_bounds__(TC_P_THREADS, 1) lstm_tc_kernel(ic3_policy_cfg
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 8 && lane == 0) {
+  if (warp == EPI_WARPS && lane == 0) {
     // ===== producer =====
     uint32_t g = 0;
     bool ok = true;
@@ -344,7 +346,7 @@ __global__ void __launch_bounds__(TC_P_THREADS, 1) lstm_tc_kernel(ic3_policy_cfg
         bulk_g2s(dst + A_CHUNK_BYTES, b_src + (size_t)c * B_CHUNK_BYTES, B_CHUNK_BYTES, bar_full + 8 * s);
       }
     }
-  } else if (warp == 9 && lane == 0) {
+  } else if (warp == EPI_WARPS + 1 && lane == 0) {
     // ===== MMA issuer =====
     // instruction descriptor: D = f32 (bits 4-5 = 1), A = B = f16 (0), K-major both, N >> 3 at 17, M >> 4 at 24
     const uint32_t idesc = (1u << 4) | ((uint32_t)(TC_NH >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
@@ -375,9 +377,9 @@ __global__ void __launch_bounds__(TC_P_THREADS, 1) lstm_tc_kernel(ic3_policy_cfg
       }
       tc_commit(bar_tfull + 8 * acc);      // accumulator complete
     }
-  } else if (warp < 8) {
-    // ===== epilogue: thread = (row of the tile, 32 hidden units) =====
-    const int quarter = warp & 3, chalf = warp >> 2;
+  } else if (warp < EPI_WARPS) {
+    // ===== epilogue: thread = (row of the tile, 16 hidden units) =====
+    const int quarter = warp & 3, cq = warp >> 2;
     const int r = quarter * 32 + lane;
     const int R = cfg.B * cfg.N;
     uint32_t li = 0;
@@ -385,26 +387,33 @@ __global__ void __launch_bounds__(TC_P_THREADS, 1) lstm_tc_kernel(ic3_policy_cfg
     for (int item = blockIdx.x; item < nitems; item += gridDim.x, ++li) {
       const int tile = item >> 1, nh = item & 1;
       const uint32_t acc = li & 1;
+      const int row = tile * TC_M + r;
+      const bool inrange = row < R;
+      bool fr = false;
+      if (inrange && io.fresh) fr = io.fresh[row / cfg.N] != 0;
+      const int ubase = nh * (TC_NH / 4) + cq * 16;
+      // previous cell state: independent of the MMAs -> fetch it while they are still running
+      float4 cold[4];
+#pragma unroll
+      for (int cg = 0; cg < 4; ++cg) {
+        cold[cg] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (inrange && !fr) cold[cg] = *reinterpret_cast<const float4*>(io.c + (size_t)row * TC_H + ubase + cg * 4);
+      }
       if (ok) ok = mbar_wait(bar_tfull + 8 * acc, (li >> 1) & 1, io.err);
       tc_fence_after();
-      const int row = tile * TC_M + r;
-      const bool valid = ok && row < R;
-      bool fr = false;
-      if (valid && io.fresh) fr = io.fresh[row / cfg.N] != 0;
-      const uint32_t taddr = tmem_base + acc * TC_NH + chalf * 128 + ((uint32_t)(quarter * 32) << 16);
+      const bool valid = ok && inrange;
+      const uint32_t taddr = tmem_base + acc * TC_NH + cq * 64 + ((uint32_t)(quarter * 32) << 16);
       float part[HEAD_PAD];
 #pragma unroll
       for (int o = 0; o < HEAD_PAD; ++o) part[o] = 0.f;
-#pragma unroll 2
-      for (int cg = 0; cg < 8; ++cg) {
+#pragma unroll
+      for (int cg = 0; cg < 4; ++cg) {
         uint32_t v[16];
         tmem_ld16(taddr + cg * 16, v);
         if (valid) {
-          const int u0 = nh * (TC_NH / 4) + chalf * 32 + cg * 4;
-          float4 cold = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (!fr) cold = *reinterpret_cast<const float4*>(io.c + (size_t)row * TC_H + u0);
+          const int u0 = ubase + cg * 4;
           float cn[4], hn[4];
-          const float co[4] = {cold.x, cold.y, cold.z, cold.w};
+          const float co[4] = {cold[cg].x, cold[cg].y, cold[cg].z, cold[cg].w};
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             const float4 b = __ldg(reinterpret_cast<const float4*>(bias_cat) + (u0 + j));
@@ -432,8 +441,8 @@ __global__ void __launch_bounds__(TC_P_THREADS, 1) lstm_tc_kernel(ic3_policy_cfg
       }
       tc_fence_before();
       mbar_arrive(bar_tempty + 8 * acc);   // this thread no longer reads the accumulator
-      if (partial && valid) {              // slot = (column half of the CTA item, column half of the warp)
-        float4* dst = reinterpret_cast<float4*>(partial + ((size_t)row * 4 + (nh * 2 + chalf)) * HEAD_PAD);
+      if (partial && valid) {              // slot = (column half of the CTA item, column quarter of the warp)
+        float4* dst = reinterpret_cast<float4*>(partial + ((size_t)row * NSLOT + (nh * 4 + cq)) * HEAD_PAD);
         dst[0] = make_float4(part[0], part[1], part[2], part[3]);
         dst[1] = make_float4(part[4], part[5], part[6], part[7]);
       }
@@ -441,7 +450,7 @@ __global__ void __launch_bounds__(TC_P_THREADS, 1) lstm_tc_kernel(ic3_policy_cfg
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 8) {
+  if (warp == EPI_WARPS) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
   }
 }
@@ -526,18 +535,18 @@ __global__ void __launch_bounds__(256) heads_kernel(ic3_policy_cfg cfg, ic3_poli
   }
 }
 
-// Finish the heads from the four per-slot partial logits (fixed summation order -> deterministic):
+// Finish the heads from the NSLOT per-slot partial logits (fixed summation order -> deterministic):
 // value, log-softmax per head, inverse-CDF sampling.  One thread per agent row.
 __global__ void __launch_bounds__(128) heads_finish_kernel(ic3_policy_cfg cfg, ic3_policy_packed w, ic3_policy_io io,
                                                             const float* __restrict__ partial) {
   const long row = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (row >= (long)cfg.B * cfg.N) return;
   float logit[HEAD_PAD];
-  const float4* p4 = reinterpret_cast<const float4*>(partial + (size_t)row * 4 * HEAD_PAD);
+  const float4* p4 = reinterpret_cast<const float4*>(partial + (size_t)row * NSLOT * HEAD_PAD);
   {
     float4 a = p4[0], b = p4[1];
 #pragma unroll
-    for (int sl = 1; sl < 4; ++sl) {
+    for (int sl = 1; sl < NSLOT; ++sl) {
       const float4 c = p4[2 * sl], d = p4[2 * sl + 1];
       a.x += c.x; a.y += c.y; a.z += c.z; a.w += c.w;
       b.x += d.x; b.y += d.y; b.z += d.z; b.w += d.w;
@@ -596,8 +605,8 @@ uint64_t ic3_tc_workspace_bytes(const ic3_policy_cfg* cfg) {
   if (!cfg || cfg->H != TC_H) return 0;
   const long R = (long)cfg->B * cfg->N;
   const long ntiles = (R + TC_M - 1) / TC_M;
-  // operand image + per-slot partial logits [R][4][HEAD_PAD]
-  return (uint64_t)ntiles * TC_NCHUNK * A_CHUNK_BYTES + (uint64_t)R * 4 * HEAD_PAD * sizeof(float);
+  // operand image + per-slot partial logits [R][NSLOT][HEAD_PAD]
+  return (uint64_t)ntiles * TC_NCHUNK * A_CHUNK_BYTES + (uint64_t)R * NSLOT * HEAD_PAD * sizeof(float);
 }
 
 int ic3_tc_pack(const ic3_policy_cfg* cfg, const ic3_policy_params* p, const ic3_policy_packed* out, cudaStream_t s) {
