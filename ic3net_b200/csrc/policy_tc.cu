@@ -224,10 +224,33 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
                "l"(src), "r"(bytes), "r"(bar)
                : "memory");
 }
+// multicast variant: the bytes land at the same shared-memory offset of every CTA in `mask`, and complete_tx
+// is signalled on the mbarrier at the same offset of each destination CTA
+__device__ __forceinline__ void bulk_g2s_mc(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;" ::"r"(dst),
+      "l"(src), "r"(bytes), "r"(bar), "h"(mask)
+      : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// same, arriving on the mbarrier at this offset in every CTA of `mask` (stage release across a cluster)
+__device__ __forceinline__ void tc_commit_mc(uint32_t bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+               "h"(mask)
+               : "memory");
 }
 // D[tmem] (+)= A[smem] . B[smem]^T, kind::f16 (fp16 inputs, fp32 accumulate), one CTA
 __device__ __forceinline__ void tc_mma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
@@ -280,12 +303,19 @@ __device__ __forceinline__ float tanh_fast(float v) {
 //                      overlaps the MMAs of item i+1
 // Work item = (128-row tile, 256-column half); item 2t and 2t+1 share the A tile (second read hits L2).
 constexpr int NSTAGE_P = 4;
+#ifndef TC_CLUSTER
+#define TC_CLUSTER 2                 // CTAs per cluster sharing the weight stream
+#endif
 constexpr int HEAD_PAD = 8;          // outputs (value + action logits) the fused epilogue supports
 constexpr int EPI_WARPS = 16;        // 4 warps per TMEM lane quarter, 64 accumulator columns (16 hidden units) each
 constexpr int EPI_THREADS = EPI_WARPS * 32;
 constexpr int TC_P_THREADS = EPI_THREADS + 64;   // + producer warp + MMA warp
 constexpr int NSLOT = 8;             // partial-logit slots per row: (column half of the item) x (column quarter of the warp)
 
+// CL = thread-block cluster size.  The CL CTAs of a cluster work on CL consecutive row tiles and the SAME
+// column half, so they consume identical weight (B) chunks: each CTA fetches 1/CL of every chunk and multicasts
+// it to all peers; a stage is recycled when the MMAs of ALL peers have released it (multicast commit).
+template <int CL>
 __global__ void __launch_bounds__(TC_P_THREADS, 1) lstm_tc_kernel(ic3_policy_cfg cfg, ic3_policy_io io,
                                                                  const __half* __restrict__ a_img,
                                                                  const __half* __restrict__ b_img,
@@ -307,11 +337,14 @@ __global__ void __launch_bounds__(TC_P_THREADS, 1) lstm_tc_kernel(ic3_policy_cfg
   const uint32_t bar_full = smem_u32(bars), bar_empty = smem_u32(bars + NSTAGE_P);
   const uint32_t bar_tfull = smem_u32(bars + 2 * NSTAGE_P), bar_tempty = smem_u32(bars + 2 * NSTAGE_P + 2);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int rank = CL > 1 ? (int)cluster_ctarank() : 0;
+  const int cl = blockIdx.x / CL, ncl = gridDim.x / CL;     // this cluster / clusters in the grid
+  constexpr uint16_t CMASK = (uint16_t)((1u << CL) - 1u);
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < NSTAGE_P; ++s) {
       mbar_init(bar_full + 8 * s, 1);
-      mbar_init(bar_empty + 8 * s, 1);
+      mbar_init(bar_empty + 8 * s, CL);        // one release from the MMA warp of every CTA in the cluster
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(bar_tfull + 8 * a, 1);
@@ -326,6 +359,7 @@ __global__ void __launch_bounds__(TC_P_THREADS, 1) lstm_tc_kernel(ic3_policy_cfg
   }
   tc_fence_before();
   __syncthreads();
+  if (CL > 1) cluster_sync_all();              // peers' barriers are initialised before anything is multicast
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -333,8 +367,8 @@ __global__ void __launch_bounds__(TC_P_THREADS, 1) lstm_tc_kernel(ic3_policy_cfg
     // ===== producer =====
     uint32_t g = 0;
     bool ok = true;
-    for (int item = blockIdx.x; item < nitems && ok; item += gridDim.x) {
-      const int tile = item >> 1, nh = item & 1;
+    for (int item = cl; item < nitems && ok; item += ncl) {
+      const int tile = (item >> 1) * CL + rank, nh = item & 1;
       const unsigned char* a_src = reinterpret_cast<const unsigned char*>(a_img) + (size_t)tile * TC_NCHUNK * A_CHUNK_BYTES;
       const unsigned char* b_src = reinterpret_cast<const unsigned char*>(b_img) + (size_t)nh * TC_NCHUNK * B_CHUNK_BYTES;
       for (int c = 0; c < TC_NCHUNK && ok; ++c, ++g) {
@@ -343,7 +377,13 @@ __global__ void __launch_bounds__(TC_P_THREADS, 1) lstm_tc_kernel(ic3_policy_cfg
         const uint32_t dst = smem_u32(smem + s * STAGE_BYTES);
         mbar_expect_tx(bar_full + 8 * s, STAGE_BYTES);
         bulk_g2s(dst, a_src + (size_t)c * A_CHUNK_BYTES, A_CHUNK_BYTES, bar_full + 8 * s);
-        bulk_g2s(dst + A_CHUNK_BYTES, b_src + (size_t)c * B_CHUNK_BYTES, B_CHUNK_BYTES, bar_full + 8 * s);
+        if (CL == 1) {
+          bulk_g2s(dst + A_CHUNK_BYTES, b_src + (size_t)c * B_CHUNK_BYTES, B_CHUNK_BYTES, bar_full + 8 * s);
+        } else {      // my 1/CL slice of the weight chunk, delivered to every CTA of the cluster
+          constexpr uint32_t SL = B_CHUNK_BYTES / CL;
+          bulk_g2s_mc(dst + A_CHUNK_BYTES + rank * SL, b_src + (size_t)c * B_CHUNK_BYTES + (size_t)rank * SL, SL,
+                      bar_full + 8 * s, CMASK);
+        }
       }
     }
   } else if (warp == EPI_WARPS + 1 && lane == 0) {
@@ -352,7 +392,7 @@ __global__ void __launch_bounds__(TC_P_THREADS, 1) lstm_tc_kernel(ic3_policy_cfg
     const uint32_t idesc = (1u << 4) | ((uint32_t)(TC_NH >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
     uint32_t g = 0, li = 0;
     bool ok = true;
-    for (int item = blockIdx.x; item < nitems && ok; item += gridDim.x, ++li) {
+    for (int item = cl; item < nitems && ok; item += ncl, ++li) {
       const uint32_t acc = li & 1;
       ok = mbar_wait(bar_tempty + 8 * acc, ((li >> 1) & 1) ^ 1, io.err);   // epilogue drained this accumulator
       tc_fence_after();
@@ -373,7 +413,8 @@ __global__ void __launch_bounds__(TC_P_THREADS, 1) lstm_tc_kernel(ic3_policy_cfg
           tc_mma_f16(tmem_d, da_lo, db_hi, idesc, 1);
           tc_mma_f16(tmem_d, da_hi, db_lo, idesc, 1);
         }
-        tc_commit(bar_empty + 8 * s);      // frees the stage when these MMAs have read it
+        if (CL == 1) tc_commit(bar_empty + 8 * s);      // frees the stage when these MMAs have read it
+        else tc_commit_mc(bar_empty + 8 * s, CMASK);    // ... in every CTA of the cluster
       }
       tc_commit(bar_tfull + 8 * acc);      // accumulator complete
     }
@@ -384,8 +425,8 @@ __global__ void __launch_bounds__(TC_P_THREADS, 1) lstm_tc_kernel(ic3_policy_cfg
     const int R = cfg.B * cfg.N;
     uint32_t li = 0;
     bool ok = true;
-    for (int item = blockIdx.x; item < nitems; item += gridDim.x, ++li) {
-      const int tile = item >> 1, nh = item & 1;
+    for (int item = cl; item < nitems; item += ncl, ++li) {
+      const int tile = (item >> 1) * CL + rank, nh = item & 1;
       const uint32_t acc = li & 1;
       const int row = tile * TC_M + r;
       const bool inrange = row < R;
@@ -450,6 +491,7 @@ __global__ void __launch_bounds__(TC_P_THREADS, 1) lstm_tc_kernel(ic3_policy_cfg
   }
   tc_fence_before();
   __syncthreads();
+  if (CL > 1) cluster_sync_all();              // no peer may still multicast into / arrive on this CTA
   if (warp == EPI_WARPS) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
   }
@@ -605,8 +647,9 @@ uint64_t ic3_tc_workspace_bytes(const ic3_policy_cfg* cfg) {
   if (!cfg || cfg->H != TC_H) return 0;
   const long R = (long)cfg->B * cfg->N;
   const long ntiles = (R + TC_M - 1) / TC_M;
+  const long ntiles_pad = (ntiles + TC_CLUSTER - 1) / TC_CLUSTER * TC_CLUSTER;   // whole clusters of tiles
   // operand image + per-slot partial logits [R][NSLOT][HEAD_PAD]
-  return (uint64_t)ntiles * TC_NCHUNK * A_CHUNK_BYTES + (uint64_t)R * NSLOT * HEAD_PAD * sizeof(float);
+  return (uint64_t)ntiles_pad * TC_NCHUNK * A_CHUNK_BYTES + (uint64_t)R * NSLOT * HEAD_PAD * sizeof(float);
 }
 
 int ic3_tc_pack(const ic3_policy_cfg* cfg, const ic3_policy_params* p, const ic3_policy_packed* out, cudaStream_t s) {
@@ -622,30 +665,52 @@ int ic3_tc_policy_step(const ic3_policy_cfg* cfg, const ic3_policy_packed* w, co
   if (!io->workspace || !w->lstm_img || !w->bias_cat) return IC3_E_NULL;
   const long R = (long)cfg->B * cfg->N;
   const int ntiles = (int)((R + TC_M - 1) / TC_M);
+  const int ntiles_pad = (ntiles + TC_CLUSTER - 1) / TC_CLUSTER * TC_CLUSTER;   // padding tiles are written as zeros
   __half* img = reinterpret_cast<__half*>(io->workspace);
-  prep_kernel<<<2 * ntiles, 256, 0, s>>>(*cfg, *io, img);
+  prep_kernel<<<2 * ntiles_pad, 256, 0, s>>>(*cfg, *io, img);
   IC3_LAUNCH_CHECK();
   const size_t smem = NSTAGE_P * STAGE_BYTES + 256 + TC_H * HEAD_PAD * sizeof(float);
   int nout = 1;
   for (int k = 0; k < cfg->nheads; ++k) nout += cfg->head_dim[k];
   const bool fused_heads = nout <= HEAD_PAD;
   float* partial = fused_heads ? reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(io->workspace) +
-                                                           (size_t)ntiles * TC_NCHUNK * A_CHUNK_BYTES)
+                                                           (size_t)ntiles_pad * TC_NCHUNK * A_CHUNK_BYTES)
                                : nullptr;
-  static int num_sms = 0;
-  if (num_sms == 0) {
-    cudaError_t e = cudaFuncSetAttribute(lstm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  static int max_clusters = 0;
+  auto kern = lstm_tc_kernel<TC_CLUSTER>;
+  if (max_clusters == 0) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
-    int dev = 0;
-    cudaGetDevice(&dev);
-    e = cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
-    if (e != cudaSuccess || num_sms <= 0) return e != cudaSuccess ? (int)e : IC3_E_RANGE;
+    cudaLaunchConfig_t q{};
+    q.gridDim = dim3(TC_CLUSTER * 148);
+    q.blockDim = dim3(TC_P_THREADS);
+    q.dynamicSmemBytes = smem;
+    cudaLaunchAttribute qa[1];
+    qa[0].id = cudaLaunchAttributeClusterDimension;
+    qa[0].val.clusterDim.x = TC_CLUSTER; qa[0].val.clusterDim.y = 1; qa[0].val.clusterDim.z = 1;
+    q.attrs = qa; q.numAttrs = 1;
+    e = cudaOccupancyMaxActiveClusters(&max_clusters, kern, &q);   // clusters that can be co-resident (persistent grid)
+    if (e != cudaSuccess || max_clusters <= 0) return e != cudaSuccess ? (int)e : IC3_E_RANGE;
   }
-  const int nitems = 2 * ntiles;
-  const int grid = nitems < num_sms ? nitems : num_sms;
-  lstm_tc_kernel<<<grid, TC_P_THREADS, smem, s>>>(*cfg, *io, img, reinterpret_cast<const __half*>(w->lstm_img),
-                                                   w->bias_cat, nitems, w->head_w, nout, partial);
-  IC3_LAUNCH_CHECK();
+  const int nitems = 2 * (ntiles_pad / TC_CLUSTER);               // (tile group, column half)
+  const int nclusters = nitems < max_clusters ? nitems : max_clusters;
+  cudaLaunchConfig_t lc{};
+  lc.gridDim = dim3(nclusters * TC_CLUSTER);
+  lc.blockDim = dim3(TC_P_THREADS);
+  lc.dynamicSmemBytes = smem;
+  lc.stream = s;
+  cudaLaunchAttribute la[1];
+  la[0].id = cudaLaunchAttributeClusterDimension;
+  la[0].val.clusterDim.x = TC_CLUSTER; la[0].val.clusterDim.y = 1; la[0].val.clusterDim.z = 1;
+  lc.attrs = la; lc.numAttrs = 1;
+  {
+    const __half* b_img = reinterpret_cast<const __half*>(w->lstm_img);
+    const __half* a_img = img;
+    cudaError_t e = cudaLaunchKernelEx(&lc, kern, *cfg, *io, a_img, b_img, (const float*)w->bias_cat, nitems,
+                                       (const float*)w->head_w, nout, partial);
+    ++g_ic3_launches;
+    if (e != cudaSuccess) return (int)e;
+  }
   if (fused_heads) {
     heads_finish_kernel<<<(int)((R + 127) / 128), 128, 0, s>>>(*cfg, *w, *io, partial);
     IC3_LAUNCH_CHECK();
