@@ -23,6 +23,8 @@
 //   heads kernel  value / action heads + sampling from h' (warp per row).
 #include <cuda_fp16.h>
 
+#include <cstdlib>
+
 #include "ic3_common.cuh"
 #include "policy_heads.cuh"
 #include "policy_internal.h"
@@ -303,9 +305,6 @@ __device__ __forceinline__ float tanh_fast(float v) {
 //                      overlaps the MMAs of item i+1
 // Work item = (128-row tile, 256-column half); item 2t and 2t+1 share the A tile (second read hits L2).
 constexpr int NSTAGE_P = 4;
-#ifndef TC_CLUSTER
-#define TC_CLUSTER 2                 // CTAs per cluster sharing the weight stream
-#endif
 constexpr int HEAD_PAD = 8;          // outputs (value + action logits) the fused epilogue supports
 constexpr int EPI_WARPS = 16;        // 4 warps per TMEM lane quarter, 64 accumulator columns (16 hidden units) each
 constexpr int EPI_THREADS = EPI_WARPS * 32;
@@ -643,11 +642,59 @@ __global__ void __launch_bounds__(128) heads_finish_kernel(ic3_policy_cfg cfg, i
 
 }  // namespace
 
+// Cluster size of the tensor-core kernel (CTAs sharing one weight stream).  Measured on B200: 1, 2 and 4 run at
+// the same speed (L2 already merges identical requests of neighbouring SMs), so 1 is the default; IC3_TC_CLUSTER
+// overrides it for experiments.
+static int tc_cluster_size() {
+  static int v = 0;
+  if (v == 0) {
+    const char* e = getenv("IC3_TC_CLUSTER");
+    v = e ? atoi(e) : 1;
+    if (v != 1 && v != 2 && v != 4 && v != 8) v = 1;
+  }
+  return v;
+}
+constexpr int TC_TILE_PAD = 8;   // tiles are padded to whole clusters of up to 8
+
+template <int CL>
+static int launch_lstm(const ic3_policy_cfg* cfg, const ic3_policy_io* io, const ic3_policy_packed* w, const __half* a_img,
+                       int ntiles_pad, size_t smem, int nout, float* partial, cudaStream_t s) {
+  static int max_clusters = 0;
+  auto kern = lstm_tc_kernel<CL>;
+  cudaLaunchAttribute la[1];
+  la[0].id = cudaLaunchAttributeClusterDimension;
+  la[0].val.clusterDim.x = CL; la[0].val.clusterDim.y = 1; la[0].val.clusterDim.z = 1;
+  if (max_clusters == 0) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    cudaLaunchConfig_t q{};
+    q.gridDim = dim3(CL * 148);
+    q.blockDim = dim3(TC_P_THREADS);
+    q.dynamicSmemBytes = smem;
+    q.attrs = la; q.numAttrs = 1;
+    e = cudaOccupancyMaxActiveClusters(&max_clusters, kern, &q);   // clusters that can be co-resident (persistent grid)
+    if (e != cudaSuccess || max_clusters <= 0) return e != cudaSuccess ? (int)e : IC3_E_RANGE;
+  }
+  const int nitems = 2 * (ntiles_pad / CL);                        // (tile group, column half)
+  const int nclusters = nitems < max_clusters ? nitems : max_clusters;
+  cudaLaunchConfig_t lc{};
+  lc.gridDim = dim3(nclusters * CL);
+  lc.blockDim = dim3(TC_P_THREADS);
+  lc.dynamicSmemBytes = smem;
+  lc.stream = s;
+  lc.attrs = la; lc.numAttrs = 1;
+  const __half* b_img = reinterpret_cast<const __half*>(w->lstm_img);
+  cudaError_t e = cudaLaunchKernelEx(&lc, kern, *cfg, *io, a_img, b_img, (const float*)w->bias_cat, nitems,
+                                     (const float*)w->head_w, nout, partial);
+  ++g_ic3_launches;
+  return e == cudaSuccess ? IC3_OK : (int)e;
+}
+
 uint64_t ic3_tc_workspace_bytes(const ic3_policy_cfg* cfg) {
   if (!cfg || cfg->H != TC_H) return 0;
   const long R = (long)cfg->B * cfg->N;
   const long ntiles = (R + TC_M - 1) / TC_M;
-  const long ntiles_pad = (ntiles + TC_CLUSTER - 1) / TC_CLUSTER * TC_CLUSTER;   // whole clusters of tiles
+  const long ntiles_pad = (ntiles + TC_TILE_PAD - 1) / TC_TILE_PAD * TC_TILE_PAD;   // whole clusters of tiles
   // operand image + per-slot partial logits [R][NSLOT][HEAD_PAD]
   return (uint64_t)ntiles_pad * TC_NCHUNK * A_CHUNK_BYTES + (uint64_t)R * NSLOT * HEAD_PAD * sizeof(float);
 }
@@ -665,7 +712,7 @@ int ic3_tc_policy_step(const ic3_policy_cfg* cfg, const ic3_policy_packed* w, co
   if (!io->workspace || !w->lstm_img || !w->bias_cat) return IC3_E_NULL;
   const long R = (long)cfg->B * cfg->N;
   const int ntiles = (int)((R + TC_M - 1) / TC_M);
-  const int ntiles_pad = (ntiles + TC_CLUSTER - 1) / TC_CLUSTER * TC_CLUSTER;   // padding tiles are written as zeros
+  const int ntiles_pad = (ntiles + TC_TILE_PAD - 1) / TC_TILE_PAD * TC_TILE_PAD;   // padding tiles are written as zeros
   __half* img = reinterpret_cast<__half*>(io->workspace);
   prep_kernel<<<2 * ntiles_pad, 256, 0, s>>>(*cfg, *io, img);
   IC3_LAUNCH_CHECK();
@@ -676,41 +723,14 @@ int ic3_tc_policy_step(const ic3_policy_cfg* cfg, const ic3_policy_packed* w, co
   float* partial = fused_heads ? reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(io->workspace) +
                                                            (size_t)ntiles_pad * TC_NCHUNK * A_CHUNK_BYTES)
                                : nullptr;
-  static int max_clusters = 0;
-  auto kern = lstm_tc_kernel<TC_CLUSTER>;
-  if (max_clusters == 0) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return (int)e;
-    cudaLaunchConfig_t q{};
-    q.gridDim = dim3(TC_CLUSTER * 148);
-    q.blockDim = dim3(TC_P_THREADS);
-    q.dynamicSmemBytes = smem;
-    cudaLaunchAttribute qa[1];
-    qa[0].id = cudaLaunchAttributeClusterDimension;
-    qa[0].val.clusterDim.x = TC_CLUSTER; qa[0].val.clusterDim.y = 1; qa[0].val.clusterDim.z = 1;
-    q.attrs = qa; q.numAttrs = 1;
-    e = cudaOccupancyMaxActiveClusters(&max_clusters, kern, &q);   // clusters that can be co-resident (persistent grid)
-    if (e != cudaSuccess || max_clusters <= 0) return e != cudaSuccess ? (int)e : IC3_E_RANGE;
+  int rc = IC3_E_RANGE;
+  switch (tc_cluster_size()) {
+    case 1: rc = launch_lstm<1>(cfg, io, w, img, ntiles_pad, smem, nout, partial, s); break;
+    case 2: rc = launch_lstm<2>(cfg, io, w, img, ntiles_pad, smem, nout, partial, s); break;
+    case 4: rc = launch_lstm<4>(cfg, io, w, img, ntiles_pad, smem, nout, partial, s); break;
+    case 8: rc = launch_lstm<8>(cfg, io, w, img, ntiles_pad, smem, nout, partial, s); break;
   }
-  const int nitems = 2 * (ntiles_pad / TC_CLUSTER);               // (tile group, column half)
-  const int nclusters = nitems < max_clusters ? nitems : max_clusters;
-  cudaLaunchConfig_t lc{};
-  lc.gridDim = dim3(nclusters * TC_CLUSTER);
-  lc.blockDim = dim3(TC_P_THREADS);
-  lc.dynamicSmemBytes = smem;
-  lc.stream = s;
-  cudaLaunchAttribute la[1];
-  la[0].id = cudaLaunchAttributeClusterDimension;
-  la[0].val.clusterDim.x = TC_CLUSTER; la[0].val.clusterDim.y = 1; la[0].val.clusterDim.z = 1;
-  lc.attrs = la; lc.numAttrs = 1;
-  {
-    const __half* b_img = reinterpret_cast<const __half*>(w->lstm_img);
-    const __half* a_img = img;
-    cudaError_t e = cudaLaunchKernelEx(&lc, kern, *cfg, *io, a_img, b_img, (const float*)w->bias_cat, nitems,
-                                       (const float*)w->head_w, nout, partial);
-    ++g_ic3_launches;
-    if (e != cudaSuccess) return (int)e;
-  }
+  if (rc) return rc;
   if (fused_heads) {
     heads_finish_kernel<<<(int)((R + 127) / 128), 128, 0, s>>>(*cfg, *w, *io, partial);
     IC3_LAUNCH_CHECK();
