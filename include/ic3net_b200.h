@@ -23,7 +23,7 @@
  *     multi_processing.py:7).
  *
  * Randomness: counter-based Philox4x32-10, key = seed, counter =
- * (env_id0 + env, tick, stream, index); see ic3net_b200/csrc/ic3_rng.cuh.  Every
+ * (env_id0 + env, tick, stream, index); see ic3net_b200/csrc/ic3_common.cuh.  Every
  * stochastic entry point also accepts explicit 24-bit draws ("tape") instead.
  */
 #ifndef IC3NET_B200_H
