@@ -224,12 +224,28 @@ def gpu_arm(opts):
 
     chunk = a.max_steps                                      # record buffers hold one episode horizon
 
+    graphs, graph_launches, replayed = {}, {}, [0]
+
     def enqueue(trn, steps):
         done = 0
         while done < steps:                                  # episode-horizon chunks reuse the record buffers
             n = min(chunk, steps - done)
-            trn._enqueue(n)
+            if opts.graph and n == chunk and id(trn) in graphs:
+                graphs[id(trn)].replay()                     # one CUDA-graph launch per episode horizon
+                replayed[0] += graph_launches[id(trn)]
+            else:
+                trn._enqueue(n)
             done += n
+
+    def capture(trn):
+        """Capture one episode horizon of the rollout (all kernels of `chunk` lock-step iterations) once."""
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        l0 = _lib.launch_count()
+        with torch.cuda.graph(g):
+            trn._enqueue(chunk)
+        graphs[id(trn)] = g
+        graph_launches[id(trn)] = _lib.launch_count() - l0   # kernels inside one replay
 
     def timed_rollout(trn, steps):
         """Enqueue `steps` lock-step iterations (+ the per-update gradient all-reduce); device events."""
@@ -245,10 +261,13 @@ def gpu_arm(opts):
     tr._alloc(chunk)
     env.env.reset(want_obs=False) if a.env_name == "predator_prey" else env.env.reset(0, want_obs=False)
     enqueue(tr, W)
+    if opts.graph:
+        capture(tr)
+        enqueue(tr, chunk)
     if world > 1:
         dist.all_reduce(grad_flat)
     torch.cuda.synchronize()
-    launches0 = _lib.launch_count()
+    launches0 = _lib.launch_count() + replayed[0]
     with ClockSampler(local) as clk:
         if world > 1:
             dist.barrier()
@@ -261,7 +280,7 @@ def gpu_arm(opts):
             dist.barrier()
         ms = e0.elapsed_time(e1)
         time.sleep(0.2)
-    launches = _lib.launch_count() - launches0
+    launches = _lib.launch_count() + replayed[0] - launches0
     t = torch.tensor([ms], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -312,6 +331,9 @@ def gpu_arm(opts):
             tr2._alloc(chunk)
             env2.env.reset(want_obs=False) if is_pp else env2.env.reset(0, want_obs=False)
             enqueue(tr2, W)
+            if opts.graph:
+                capture(tr2)
+                enqueue(tr2, chunk)
             torch.cuda.synchronize()
             f0, f1 = timed_rollout(tr2, K)
             torch.cuda.synchronize()
@@ -332,6 +354,7 @@ def gpu_arm(opts):
                     data="synthetic",
                     config=dict(workload=opts.workload, envs_per_gpu=B, nagents=N, obs_dim=O, hid_size=H,
                                 max_steps=a.max_steps, obs_mode=opts.obs_mode, parallelism="dp%d" % world,
+                                cuda_graph=bool(opts.graph), policy_impl=net.policy_impl,
                                 l2="per-step working set %.2f GB > 126 MB L2 (inputs larger than L2)"
                                    % ((8 * O + 20 * H) * B * N / 1e9),
                                 weights="random init (torch.manual_seed(0)), reference architecture"),
@@ -510,6 +533,7 @@ def main():
     ap.add_argument("--obs_mode", default="dense", choices=["dense", "index"])
     ap.add_argument("--policy_impl", default=None, choices=["tc", "simt"],
                     help="tcgen05 tensor-core policy kernels (default for hid_size 128) or the fp32 SIMT kernel")
+    ap.add_argument("--graph", action="store_true", help="replay each episode horizon of the rollout as one CUDA graph")
     ap.add_argument("--quick", action="store_true", help="skip the e2e / index / CPU legs (profiling runs)")
     opts = ap.parse_args()
     if opts.impl == "reference":
