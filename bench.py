@@ -393,6 +393,13 @@ def per_kernel_times(tr, a, env, net, steps, C, torch, _lib):
         e1.record()
         ev.setdefault(name, []).append((e0, e1))
 
+    ws = net.workspace(B)[0]
+    W_ = 2 * e.vision + 1
+    fused_x = tr.obs_mode != "dense" and ws is not None and W_ * W_ <= 25     # index encoder fused into the policy step
+    src = {}
+    if fused_x:
+        src = dict(tj_env=C.addressof(e.cfg), tj_state=C.addressof(e.state)) if is_tj else \
+            dict(pp_env=C.addressof(e.cfg), pp_state=C.addressof(e.state))
     for t in range(steps):
         if tr.obs_mode == "dense":
             if is_tj:
@@ -401,18 +408,20 @@ def per_kernel_times(tr, a, env, net, steps, C, torch, _lib):
                 timed("obs_gather", lambda: lib.ic3_pp_obs(C.byref(e.cfg), C.byref(e.state), b["obs"].data_ptr(), s))
             timed("encoder_dense", lambda: lib.ic3_encoder_dense(C.byref(cfg), C.byref(w), b["obs"].data_ptr(),
                                                                  b["x"].data_ptr(), s))
+        elif fused_x:
+            pass
         elif is_tj:
             timed("encoder_index", lambda: lib.ic3_tj_encoder_index(C.byref(e.cfg), C.byref(e.state), C.byref(cfg),
                                                                     C.byref(w), b["x"].data_ptr(), s))
         else:
             timed("encoder_index", lambda: lib.ic3_pp_encoder_index(C.byref(e.cfg), C.byref(e.state), C.byref(cfg),
                                                                     C.byref(w), b["x"].data_ptr(), s))
-        io = _lib.PolicyIO(x=b["x"].data_ptr(), h=b["h"].data_ptr(), c=b["c"].data_ptr(),
+        io = _lib.PolicyIO(x=None if fused_x else b["x"].data_ptr(), h=b["h"].data_ptr(), c=b["c"].data_ptr(),
                            comm_action=b["comm"].data_ptr() if hard else None, alive=b["alive"].data_ptr(),
                            fresh=b["fresh"].data_ptr(), tick=e.tick.data_ptr(), draws=None, h_out=b["h"].data_ptr(),
                            c_out=b["c"].data_ptr(), value=b["value"][t].data_ptr(), logp=b["logp"][t].data_ptr(),
-                           action=b["action"][t].data_ptr(), workspace=_lib.ptr(net.workspace(B)[0]),
-                           err=b["err"].data_ptr())
+                           action=b["action"][t].data_ptr(), workspace=_lib.ptr(ws),
+                           err=b["err"].data_ptr(), **src)
         timed("policy_step", lambda: lib.ic3_policy_step(C.byref(cfg), C.byref(w), C.byref(io), s))
         r = _lib.RolloutIO(t=t, max_steps=a.max_steps, nheads=nh, hard_attn=hard,
                            comm_action_one=int(bool(a.comm_action_one)), last=0, action=b["action"][t].data_ptr(),

@@ -621,11 +621,12 @@ extern "C" int ic3_policy_step(const ic3_policy_cfg* cfg, const ic3_policy_packe
   if (rc) return rc;
   rc = packed_check(w);
   if (rc) return rc;
-  if (!io || !io->x || !io->h || !io->c || !io->h_out || !io->c_out || !io->value || !io->logp) return IC3_E_NULL;
+  if (!io || !io->h || !io->c || !io->h_out || !io->c_out || !io->value || !io->logp) return IC3_E_NULL;
   if (cfg->hard_attn && !io->comm_action) return IC3_E_NULL;
   if (cfg->N > ROWS) return IC3_E_RANGE;
   if (io->workspace && w->lstm_img)       // tcgen05 path (policy_tc.cu); otherwise the fp32 SIMT kernel below
     return ic3_tc_policy_step(cfg, w, io, (cudaStream_t)stream);
+  if (!io->x) return IC3_E_NULL;
   PolicyArgs a{*cfg, *w, *io};
   IC3_DISPATCH_H(cfg->H, launch_policy<HH>(a, (cudaStream_t)stream));
 }

@@ -24,6 +24,7 @@
 #include <cuda_fp16.h>
 
 #include <cstdlib>
+#include <cstring>
 
 #include "ic3_common.cuh"
 #include "policy_heads.cuh"
@@ -115,11 +116,35 @@ __global__ void pack_tc_kernel(ic3_policy_params p, __half* __restrict__ img, fl
 // matrices, with S_k = g_k (T - h_k) / (n_alive - 1).
 constexpr int PREP_ROWS = 64;      // rows per CTA (half a tile): 2 x more CTAs in flight than tiles
 constexpr int PREP_MAX_ENV = 34;   // environments touching 64 rows when N >= 2
+constexpr int PREP_MAX_WW = 25;    // window cells (vision <= 2) the fused index encoder supports
 
-__global__ void __launch_bounds__(256) prep_kernel(ic3_policy_cfg cfg, ic3_policy_io io, __half* __restrict__ img) {
+// Where the encoder output x comes from: a [R,H] fp32 tensor, or -- fused index encoder -- straight from the
+// environment state (same sum, same order as *_encoder_index_kernel / encoder_dense_kernel -> bit-identical x).
+enum { XSRC_TENSOR = 0, XSRC_PP = 1, XSRC_TJ = 2 };
+struct PrepSrc {
+  ic3_pp_cfg pp;
+  ic3_pp_state pps;
+  ic3_tj_cfg tj;
+  ic3_tj_state tjs;
+  const float* wT;     // encoder.weight^T [O, H]
+  const float* bias;   // [H]
+};
+
+__device__ __forceinline__ void fma4(float4& a, float v, const float4 w) {
+  a.x = fmaf(v, w.x, a.x); a.y = fmaf(v, w.y, a.y); a.z = fmaf(v, w.z, a.z); a.w = fmaf(v, w.w, a.w);
+}
+
+template <int XSRC>
+__global__ void __launch_bounds__(256) prep_kernel(ic3_policy_cfg cfg, ic3_policy_io io, __half* __restrict__ img,
+                                                   PrepSrc src) {
   __shared__ float s_gate[PREP_ROWS + 64];
   __shared__ float s_den[PREP_ROWS + 64];
   __shared__ __align__(16) float s_T[PREP_MAX_ENV][TC_H];
+  // fused index encoder: per (row, window cell) the feature index of the one-hot class and the counts
+  __shared__ int s_feat[XSRC == XSRC_TENSOR ? 1 : PREP_ROWS * PREP_MAX_WW];
+  __shared__ int s_cnt[XSRC == XSRC_TENSOR ? 1 : PREP_ROWS * PREP_MAX_WW];
+  __shared__ float s_la[XSRC == XSRC_TJ ? PREP_ROWS : 1], s_ri[XSRC == XSRC_TJ ? PREP_ROWS : 1];
+  __shared__ int s_live[XSRC == XSRC_TJ ? PREP_ROWS : 1];
   const int N = cfg.N;
   const int R = cfg.B * N;
   const int tile = blockIdx.x >> 1, hb = blockIdx.x & 1;
@@ -144,6 +169,62 @@ __global__ void __launch_bounds__(256) prep_kernel(ic3_policy_cfg cfg, ic3_polic
     }
     s_gate[w] = g;
     s_den[w] = den;
+  }
+  if (XSRC == XSRC_PP) {          // predator_prey_env.py:188-210
+    const int D = src.pp.dim, v = src.pp.vision, W = 2 * v + 1, WW = W * W, V = D * D + 4;
+    for (int p = threadIdx.x; p < PREP_ROWS * WW; p += blockDim.x) {
+      const int rl = p / WW, w = p - rl * WW, row = row0 + rl;
+      int feat = 0, cnt = 0;
+      if (row < R) {
+        const int e = row / N, i = row - e * N;
+        const int* l = src.pps.loc + (size_t)e * (N + 1) * 2;
+        const int dy = w / W, dx = w - dy * W;
+        const int rr = l[2 * i] - v + dy, cc = l[2 * i + 1] - v + dx;
+        if (rr >= 0 && rr < D && cc >= 0 && cc < D) {
+          int npred = 0;
+          for (int j = 0; j < N; ++j) npred += (l[2 * j] == rr && l[2 * j + 1] == cc);
+          const int nprey = (l[2 * N] == rr && l[2 * N + 1] == cc);
+          feat = w * V + rr * D + cc;
+          cnt = npred | (nprey << 8);
+        } else {
+          feat = w * V + V - 3;                          // OUTSIDE class
+        }
+      }
+      s_feat[rl * WW + w] = feat;
+      s_cnt[rl * WW + w] = cnt;
+    }
+  } else if (XSRC == XSRC_TJ) {   // traffic_junction_env.py:321-366
+    const int v = src.tj.vision, W = 2 * v + 1, WW = W * W, V = src.tj.vocab;
+    for (int rl = threadIdx.x; rl < PREP_ROWS; rl += blockDim.x) {
+      const int row = row0 + rl;
+      int live = 0;
+      float la = 0.f, ri = 0.f;
+      if (row < R) {
+        live = src.tjs.alive[row] != 0;
+        la = (float)src.tjs.last_act[row];
+        ri = (float)src.tjs.route_id[row] / (float)(src.tj.npath - 1);
+      }
+      s_live[rl] = live; s_la[rl] = la; s_ri[rl] = ri;
+    }
+    for (int p = threadIdx.x; p < PREP_ROWS * WW; p += blockDim.x) {
+      const int rl = p / WW, w = p - rl * WW, row = row0 + rl;
+      int feat = 0, cnt = 0;
+      if (row < R) {
+        const int e = row / N;
+        const int* l = src.tjs.loc + (size_t)e * N * 2;
+        const int i = row - e * N;
+        const int dy = w / W, dx = w - dy * W;
+        const int rr = l[2 * i] - v + dy, cc = l[2 * i + 1] - v + dx;
+        int cls = src.tj.outside_cls;
+        if (rr >= 0 && rr < src.tj.h && cc >= 0 && cc < src.tj.w) {
+          cls = src.tj.grid[rr * src.tj.w + cc];
+          for (int j = 0; j < N; ++j) cnt += (l[2 * j] == rr && l[2 * j + 1] == cc);
+        }
+        feat = 2 + w * V + cls;
+      }
+      s_feat[rl * WW + w] = feat;
+      s_cnt[rl * WW + w] = cnt;
+    }
   }
   __syncthreads();
   const int e_first = row0 / N;
@@ -179,7 +260,30 @@ __global__ void __launch_bounds__(256) prep_kernel(ic3_policy_cfg cfg, ic3_polic
     if (row < R) {
       const int e = row / N;
       const bool fr = io.fresh && io.fresh[e];
-      xv = __ldg(reinterpret_cast<const float4*>(io.x + (size_t)row * TC_H) + q);
+      if (XSRC == XSRC_TENSOR) {
+        xv = __ldg(reinterpret_cast<const float4*>(io.x + (size_t)row * TC_H) + q);
+      } else {                                     // comm.py:119 on the one-hot observation, never materialised
+        const float4* wq = reinterpret_cast<const float4*>(src.wT) + q;       // column slice 4q..4q+3 of every W^T row
+        xv = __ldg(reinterpret_cast<const float4*>(src.bias) + q);
+        if (XSRC == XSRC_PP) {
+          const int W = 2 * src.pp.vision + 1, WW = W * W, V = src.pp.dim * src.pp.dim + 4;
+          for (int w = 0; w < WW; ++w) {
+            const int feat = s_feat[rl * WW + w], cnt = s_cnt[rl * WW + w];
+            fma4(xv, 1.f, __ldg(wq + (size_t)feat * (TC_H / 4)));
+            if (cnt >> 8) fma4(xv, (float)(cnt >> 8), __ldg(wq + (size_t)(w * V + V - 2) * (TC_H / 4)));     // PREY
+            if (cnt & 255) fma4(xv, (float)(cnt & 255), __ldg(wq + (size_t)(w * V + V - 1) * (TC_H / 4)));  // PREDATOR
+          }
+        } else if (s_live[rl]) {
+          const int W = 2 * src.tj.vision + 1, WW = W * W, V = src.tj.vocab;
+          if (s_la[rl] != 0.f) fma4(xv, s_la[rl], __ldg(wq));
+          if (s_ri[rl] != 0.f) fma4(xv, s_ri[rl], __ldg(wq + (TC_H / 4)));
+          for (int w = 0; w < WW; ++w) {
+            const int feat = s_feat[rl * WW + w], cnt = s_cnt[rl * WW + w];
+            fma4(xv, 1.f, __ldg(wq + (size_t)feat * (TC_H / 4)));
+            if (cnt) fma4(xv, (float)cnt, __ldg(wq + (size_t)(2 + w * V + src.tj.car_cls) * (TC_H / 4)));
+          }
+        }
+      }
       if (!fr) hv = __ldg(reinterpret_cast<const float4*>(io.h + (size_t)row * TC_H) + q);
       if (want_s && s_gate[rl + 32] != 0.f) {      // gate 1 => own h is part of T
         const float4 t = *reinterpret_cast<const float4*>(&s_T[e - e_first][4 * q]);
@@ -714,7 +818,29 @@ int ic3_tc_policy_step(const ic3_policy_cfg* cfg, const ic3_policy_packed* w, co
   const int ntiles = (int)((R + TC_M - 1) / TC_M);
   const int ntiles_pad = (ntiles + TC_TILE_PAD - 1) / TC_TILE_PAD * TC_TILE_PAD;   // padding tiles are written as zeros
   __half* img = reinterpret_cast<__half*>(io->workspace);
-  prep_kernel<<<2 * ntiles_pad, 256, 0, s>>>(*cfg, *io, img);
+  PrepSrc src;
+  memset(&src, 0, sizeof(src));
+  src.wT = w->enc_wT;
+  src.bias = w->enc_b;
+  if (io->x) {
+    prep_kernel<XSRC_TENSOR><<<2 * ntiles_pad, 256, 0, s>>>(*cfg, *io, img, src);
+  } else if (io->pp_env && io->pp_state) {       // fused index encoder, predator-prey
+    const int W = 2 * io->pp_env->vision + 1;
+    if (W * W > PREP_MAX_WW || io->pp_env->B != cfg->B || io->pp_env->N != cfg->N) return IC3_E_RANGE;
+    if (cfg->O != W * W * (io->pp_env->dim * io->pp_env->dim + 4)) return IC3_E_RANGE;
+    src.pp = *io->pp_env;
+    src.pps = *io->pp_state;
+    prep_kernel<XSRC_PP><<<2 * ntiles_pad, 256, 0, s>>>(*cfg, *io, img, src);
+  } else if (io->tj_env && io->tj_state) {       // fused index encoder, traffic junction
+    const int W = 2 * io->tj_env->vision + 1;
+    if (W * W > PREP_MAX_WW || io->tj_env->B != cfg->B || io->tj_env->N != cfg->N) return IC3_E_RANGE;
+    if (cfg->O != 2 + W * W * io->tj_env->vocab) return IC3_E_RANGE;
+    src.tj = *io->tj_env;
+    src.tjs = *io->tj_state;
+    prep_kernel<XSRC_TJ><<<2 * ntiles_pad, 256, 0, s>>>(*cfg, *io, img, src);
+  } else {
+    return IC3_E_NULL;
+  }
   IC3_LAUNCH_CHECK();
   const size_t smem = NSTAGE_P * STAGE_BYTES + 256 + TC_H * HEAD_PAD * sizeof(float);
   int nout = 1;

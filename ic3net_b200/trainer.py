@@ -107,6 +107,13 @@ class Trainer(object):
         ws, _ = net.workspace(B)          # tensor-core path scratch (None for the fp32 SIMT kernel)
         rec = self.record_for_grad
         dense = self.obs_mode == 'dense' or (rec and self.is_tj)
+        # tensor-core path: the index encoder is fused into the policy step (x never leaves the operand image)
+        W = 2 * e.vision + 1
+        fused_x = (not dense) and ws is not None and W * W <= 25
+        src = {}
+        if fused_x:
+            src = dict(tj_env=C.addressof(e.cfg), tj_state=C.addressof(e.state)) if self.is_tj else \
+                dict(pp_env=C.addressof(e.cfg), pp_state=C.addressof(e.state))
         for t in range(T):
             if rec:
                 b['s_fresh'][t].copy_(b['fresh'])
@@ -126,18 +133,20 @@ class Trainer(object):
                 _lib.check(lib.ic3_encoder_dense(C.byref(cfg), C.byref(w), b['obs'].data_ptr(), b['x'].data_ptr(), s))
                 if rec and self.is_tj:
                     b['s_obs'][t].copy_(b['obs'])
+            elif fused_x:
+                pass
             elif self.is_tj:
                 _lib.check(lib.ic3_tj_encoder_index(C.byref(e.cfg), C.byref(e.state), C.byref(cfg), C.byref(w),
                                                     b['x'].data_ptr(), s))
             else:
                 _lib.check(lib.ic3_pp_encoder_index(C.byref(e.cfg), C.byref(e.state), C.byref(cfg), C.byref(w),
                                                     b['x'].data_ptr(), s))
-            io = _lib.PolicyIO(x=b['x'].data_ptr(), h=b['h'].data_ptr(), c=b['c'].data_ptr(),
+            io = _lib.PolicyIO(x=None if fused_x else b['x'].data_ptr(), h=b['h'].data_ptr(), c=b['c'].data_ptr(),
                                comm_action=b['comm'].data_ptr() if hard else None, alive=b['alive'].data_ptr(),
                                fresh=b['fresh'].data_ptr(), tick=e.tick.data_ptr(), draws=None,
                                h_out=b['h'].data_ptr(), c_out=b['c'].data_ptr(), value=b['value'][t].data_ptr(),
                                logp=b['logp'][t].data_ptr(), action=b['action'][t].data_ptr(),
-                               workspace=_lib.ptr(ws), err=b['err'].data_ptr())
+                               workspace=_lib.ptr(ws), err=b['err'].data_ptr(), **src)
             _lib.check(lib.ic3_policy_step(C.byref(cfg), C.byref(w), C.byref(io), s))
             r = _lib.RolloutIO(t=t, max_steps=args.max_steps, nheads=nh, hard_attn=hard,
                                comm_action_one=int(bool(args.comm_action_one)), last=int(t == T - 1),

@@ -249,6 +249,12 @@ typedef struct {
   int32_t* action;            /* [B, N, nheads] sampled actions or NULL (action_utils.py:32-36) */
   void* workspace;            /* tcgen05 path: ic3_policy_workspace_bytes(cfg) bytes of scratch (operand images), else NULL */
   int32_t* err;               /* tcgen05 path: device flag word (pipeline watchdog), may be NULL */
+  /* tcgen05 path only: when x == NULL the encoder output is computed from the environment state inside the
+   * policy step (fused index encoder, vision <= 2); exactly one pair must then be set (HOST pointers). */
+  const ic3_pp_cfg* pp_env;
+  const ic3_pp_state* pp_state;
+  const ic3_tj_cfg* tj_env;
+  const ic3_tj_state* tj_state;
 } ic3_policy_io;
 
 /* Scratch the tcgen05 policy path needs for a batch of cfg->B environments (0 when unsupported). */
