@@ -117,6 +117,7 @@ __global__ void pack_tc_kernel(ic3_policy_params p, __half* __restrict__ img, fl
 constexpr int PREP_ROWS = 64;      // rows per CTA (half a tile): 2 x more CTAs in flight than tiles
 constexpr int PREP_MAX_ENV = 34;   // environments touching 64 rows when N >= 2
 constexpr int PREP_MAX_WW = 25;    // window cells (vision <= 2) the fused index encoder supports
+constexpr int PREP_X_BYTES = PREP_ROWS * TC_H * 4;   // shared-memory x tile of the fused index encoder
 
 // Where the encoder output x comes from: a [R,H] fp32 tensor, or -- fused index encoder -- straight from the
 // environment state (same sum, same order as *_encoder_index_kernel / encoder_dense_kernel -> bit-identical x).
@@ -145,6 +146,7 @@ __global__ void __launch_bounds__(256) prep_kernel(ic3_policy_cfg cfg, ic3_polic
   __shared__ int s_cnt[XSRC == XSRC_TENSOR ? 1 : PREP_ROWS * PREP_MAX_WW];
   __shared__ float s_la[XSRC == XSRC_TJ ? PREP_ROWS : 1], s_ri[XSRC == XSRC_TJ ? PREP_ROWS : 1];
   __shared__ int s_live[XSRC == XSRC_TJ ? PREP_ROWS : 1];
+  extern __shared__ __align__(16) float s_x[];   // [PREP_ROWS][H] encoder output (index sources only)
   const int N = cfg.N;
   const int R = cfg.B * N;
   const int tile = blockIdx.x >> 1, hb = blockIdx.x & 1;
@@ -227,6 +229,36 @@ __global__ void __launch_bounds__(256) prep_kernel(ic3_policy_cfg cfg, ic3_polic
     }
   }
   __syncthreads();
+  if (XSRC != XSRC_TENSOR) {
+    // comm.py:119 on the one-hot observation, never materialised: warp per row, lane = 4 consecutive hidden
+    // units, every weight-row read is one coalesced 512-byte request; x lands in shared memory
+    const int gw = threadIdx.x >> 5, gl = threadIdx.x & 31;
+    const float4* wq = reinterpret_cast<const float4*>(src.wT) + gl;
+    for (int rl = gw; rl < PREP_ROWS; rl += 8) {
+      float4 xv = __ldg(reinterpret_cast<const float4*>(src.bias) + gl);
+      if (row0 + rl < R) {
+        if (XSRC == XSRC_PP) {
+          const int W = 2 * src.pp.vision + 1, WW = W * W, V = src.pp.dim * src.pp.dim + 4;
+          for (int w = 0; w < WW; ++w) {
+            const int feat = s_feat[rl * WW + w], cnt = s_cnt[rl * WW + w];
+            fma4(xv, 1.f, __ldg(wq + (size_t)feat * (TC_H / 4)));
+            if (cnt >> 8) fma4(xv, (float)(cnt >> 8), __ldg(wq + (size_t)(w * V + V - 2) * (TC_H / 4)));     // PREY
+            if (cnt & 255) fma4(xv, (float)(cnt & 255), __ldg(wq + (size_t)(w * V + V - 1) * (TC_H / 4)));  // PREDATOR
+          }
+        } else if (s_live[rl]) {
+          const int W = 2 * src.tj.vision + 1, WW = W * W, V = src.tj.vocab;
+          if (s_la[rl] != 0.f) fma4(xv, s_la[rl], __ldg(wq));
+          if (s_ri[rl] != 0.f) fma4(xv, s_ri[rl], __ldg(wq + (TC_H / 4)));
+          for (int w = 0; w < WW; ++w) {
+            const int feat = s_feat[rl * WW + w], cnt = s_cnt[rl * WW + w];
+            fma4(xv, 1.f, __ldg(wq + (size_t)feat * (TC_H / 4)));
+            if (cnt) fma4(xv, (float)cnt, __ldg(wq + (size_t)(2 + w * V + src.tj.car_cls) * (TC_H / 4)));
+          }
+        }
+      }
+      *reinterpret_cast<float4*>(&s_x[rl * TC_H + 4 * gl]) = xv;
+    }
+  }
   const int e_first = row0 / N;
   const int last_row = min(R, row0 + PREP_ROWS) - 1;
   const bool want_s = !cfg.comm_mask_zero && N >= 2 && last_row >= row0;
@@ -260,30 +292,8 @@ __global__ void __launch_bounds__(256) prep_kernel(ic3_policy_cfg cfg, ic3_polic
     if (row < R) {
       const int e = row / N;
       const bool fr = io.fresh && io.fresh[e];
-      if (XSRC == XSRC_TENSOR) {
-        xv = __ldg(reinterpret_cast<const float4*>(io.x + (size_t)row * TC_H) + q);
-      } else {                                     // comm.py:119 on the one-hot observation, never materialised
-        const float4* wq = reinterpret_cast<const float4*>(src.wT) + q;       // column slice 4q..4q+3 of every W^T row
-        xv = __ldg(reinterpret_cast<const float4*>(src.bias) + q);
-        if (XSRC == XSRC_PP) {
-          const int W = 2 * src.pp.vision + 1, WW = W * W, V = src.pp.dim * src.pp.dim + 4;
-          for (int w = 0; w < WW; ++w) {
-            const int feat = s_feat[rl * WW + w], cnt = s_cnt[rl * WW + w];
-            fma4(xv, 1.f, __ldg(wq + (size_t)feat * (TC_H / 4)));
-            if (cnt >> 8) fma4(xv, (float)(cnt >> 8), __ldg(wq + (size_t)(w * V + V - 2) * (TC_H / 4)));     // PREY
-            if (cnt & 255) fma4(xv, (float)(cnt & 255), __ldg(wq + (size_t)(w * V + V - 1) * (TC_H / 4)));  // PREDATOR
-          }
-        } else if (s_live[rl]) {
-          const int W = 2 * src.tj.vision + 1, WW = W * W, V = src.tj.vocab;
-          if (s_la[rl] != 0.f) fma4(xv, s_la[rl], __ldg(wq));
-          if (s_ri[rl] != 0.f) fma4(xv, s_ri[rl], __ldg(wq + (TC_H / 4)));
-          for (int w = 0; w < WW; ++w) {
-            const int feat = s_feat[rl * WW + w], cnt = s_cnt[rl * WW + w];
-            fma4(xv, 1.f, __ldg(wq + (size_t)feat * (TC_H / 4)));
-            if (cnt) fma4(xv, (float)cnt, __ldg(wq + (size_t)(2 + w * V + src.tj.car_cls) * (TC_H / 4)));
-          }
-        }
-      }
+      if (XSRC == XSRC_TENSOR) xv = __ldg(reinterpret_cast<const float4*>(io.x + (size_t)row * TC_H) + q);
+      else xv = *reinterpret_cast<const float4*>(&s_x[rl * TC_H + 4 * q]);
       if (!fr) hv = __ldg(reinterpret_cast<const float4*>(io.h + (size_t)row * TC_H) + q);
       if (want_s && s_gate[rl + 32] != 0.f) {      // gate 1 => own h is part of T
         const float4 t = *reinterpret_cast<const float4*>(&s_T[e - e_first][4 * q]);
@@ -830,14 +840,30 @@ int ic3_tc_policy_step(const ic3_policy_cfg* cfg, const ic3_policy_packed* w, co
     if (cfg->O != W * W * (io->pp_env->dim * io->pp_env->dim + 4)) return IC3_E_RANGE;
     src.pp = *io->pp_env;
     src.pps = *io->pp_state;
-    prep_kernel<XSRC_PP><<<2 * ntiles_pad, 256, 0, s>>>(*cfg, *io, img, src);
+    {
+      static bool cfgd = false;
+      if (!cfgd) {
+        cudaError_t e = cudaFuncSetAttribute(prep_kernel<XSRC_PP>, cudaFuncAttributeMaxDynamicSharedMemorySize, PREP_X_BYTES);
+        if (e != cudaSuccess) return (int)e;
+        cfgd = true;
+      }
+    }
+    prep_kernel<XSRC_PP><<<2 * ntiles_pad, 256, PREP_X_BYTES, s>>>(*cfg, *io, img, src);
   } else if (io->tj_env && io->tj_state) {       // fused index encoder, traffic junction
     const int W = 2 * io->tj_env->vision + 1;
     if (W * W > PREP_MAX_WW || io->tj_env->B != cfg->B || io->tj_env->N != cfg->N) return IC3_E_RANGE;
     if (cfg->O != 2 + W * W * io->tj_env->vocab) return IC3_E_RANGE;
     src.tj = *io->tj_env;
     src.tjs = *io->tj_state;
-    prep_kernel<XSRC_TJ><<<2 * ntiles_pad, 256, 0, s>>>(*cfg, *io, img, src);
+    {
+      static bool cfgd = false;
+      if (!cfgd) {
+        cudaError_t e = cudaFuncSetAttribute(prep_kernel<XSRC_TJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, PREP_X_BYTES);
+        if (e != cudaSuccess) return (int)e;
+        cfgd = true;
+      }
+    }
+    prep_kernel<XSRC_TJ><<<2 * ntiles_pad, 256, PREP_X_BYTES, s>>>(*cfg, *io, img, src);
   } else {
     return IC3_E_NULL;
   }
