@@ -306,8 +306,13 @@ def gpu_arm(opts):
         roof = None
         if "obs_gather" in kern:
             ach = obs_bytes / (kern["obs_gather"] * 1e-3) / 1e9
+            traffic = None          # DRAM bytes per launch from the committed ncu --set full capture, when there is one
+            try:
+                traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))[opts.workload]["obs_gather"]
+            except Exception:
+                pass
             roof = dict(kernel="obs_gather", bound="hbm", achieved=ach, peak=hbm_peak, unit="GB/s",
-                        frac=ach / hbm_peak, traffic=None, peak_source=peak_src,
+                        frac=ach / hbm_peak, traffic=traffic, peak_source=peak_src,
                         algorithmic_bytes_per_launch=obs_bytes, avg_launch_ms=kern["obs_gather"])
         kinfo = {}
         for k, v in kern.items():

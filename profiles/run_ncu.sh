@@ -12,5 +12,5 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 500 --csv --log-fil
 ncu --set full --clock-control none --import-source on -k regex:pp_step_kernel -s 8 -c 2 -o $OUT/prof_ppstep_$TAG $B > $OUT/ncu_ppstep_$TAG.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:encoder_dense_kernel -s 4 -c 1 -o $OUT/prof_encoder_$TAG $B > $OUT/ncu_encoder_$TAG.log 2>&1
 ncu --set full --clock-control none --import-source on -k "regex:lstm_tc_kernel|policy_step_kernel" -s 4 -c 1 -o $OUT/prof_policy_$TAG $B > $OUT/ncu_policy_$TAG.log 2>&1
-ncu --set full --clock-control none --import-source on -k "regex:prep_kernel|heads_kernel" -s 8 -c 2 -o $OUT/prof_prephead_$TAG $B > $OUT/ncu_prephead_$TAG.log 2>&1
+ncu --set full --clock-control none --import-source on -k "regex:prep_kernel|heads_finish_kernel|heads_kernel" -s 8 -c 2 -o $OUT/prof_prephead_$TAG $B > $OUT/ncu_prephead_$TAG.log 2>&1
 ls -la $OUT
