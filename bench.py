@@ -202,6 +202,8 @@ def gpu_arm(opts):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"      # keep NCCL's version banner off stdout: ONE JSON line is the contract
         dist.init_process_group("nccl", device_id=dev)
     K, W = opts.steps, max(3, opts.warmup)
 
