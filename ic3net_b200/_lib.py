@@ -138,7 +138,13 @@ def ptr(t):
     return t.data_ptr()
 
 
+_raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+
+
 def stream():
+    """cudaStream_t of torch's current stream on the current device (honours stream / graph-capture contexts)."""
+    if _raw_stream is not None:          # one C call instead of building a torch.cuda.Stream object per launch
+        return _raw_stream(torch.cuda.current_device())
     return torch.cuda.current_stream().cuda_stream
 
 

@@ -23,11 +23,16 @@ from . import _lib
 
 def _as_u8(v, B, N, device):
     """info['comm_action'] / info['alive_mask'] (numpy or tensor, [N] or [B,N]) -> uint8 [B,N]."""
-    t = v if torch.is_tensor(v) else torch.as_tensor(np.asarray(v))
-    t = t.to(device)
+    if torch.is_tensor(v) and v.is_cuda:
+        t = v if v.dtype == torch.uint8 else (v != 0).to(torch.uint8)
+    else:       # host mask: normalise on the host, then ONE copy (asynchronous when the source is pinned)
+        t = v if torch.is_tensor(v) else torch.from_numpy(np.ascontiguousarray(np.asarray(v)))
+        if t.dtype != torch.uint8:
+            t = (t != 0).to(torch.uint8)
+        t = t.to(device, non_blocking=True)
     if t.dim() == 1:
         t = t.unsqueeze(0).expand(B, N)
-    return (t.reshape(B, N) != 0).to(torch.uint8).contiguous()
+    return t.reshape(B, N).contiguous()      # the kernels test `!= 0`, any non-zero byte counts as 1
 
 
 class CommNetMLP(nn.Module):
