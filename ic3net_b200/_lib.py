@@ -15,7 +15,7 @@ LIB_PATH = os.path.join(_HERE, "libic3net_b200.so")
 MAX_AGENTS = 32
 MAX_HEADS = 4
 MAX_HEAD_DIM = 16
-LSTM_IMG_BYTES = 786432
+LSTM_IMG_BYTES = 1572864
 
 ERR_EPISODE_DONE = 1
 ERR_ROUTE_OVERRUN = 2

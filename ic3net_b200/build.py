@@ -36,11 +36,12 @@ def _stale():
 def build(force=False, verbose=False):
     if not force and not _stale():
         return LIB
+    extra = os.environ.get("IC3_NVCC_EXTRA", "").split()      # profiling experiments only (e.g. -DIC3_TC_EXP_SKIP_MMA)
     objs = []
     procs = []
     for src in SOURCES:
         obj = os.path.join(CSRC, src.replace(".cu", ".o"))
-        cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
+        cmd = [_nvcc()] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + \
               ["-c", os.path.join(CSRC, src), "-o", obj]
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)))
         objs.append(obj)
@@ -50,7 +51,7 @@ def build(force=False, verbose=False):
             raise RuntimeError("nvcc failed on %s:\n%s" % (src, out))
         if verbose:
             print(out)
-    cmd = [_nvcc(), "-shared", "-o", LIB] + objs + ["-lcudart"]
+    cmd = [_nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", LIB] + objs + ["-lcudart"]
     subprocess.check_call(cmd)
     return LIB
 

@@ -56,6 +56,14 @@ __host__ __device__ __forceinline__ size_t b_img_off(int nh, int k, int n, int p
   return ((((((size_t)(nh * TC_NCHUNK + c) * 2 + part) * 4 + (kk >> 3)) * 32 + (n >> 3)) * 8 + (n & 7)) * 8) + (kk & 7);
 }
 
+constexpr size_t B_IMG_HALFS = (size_t)2 * TC_NCHUNK * B_CHUNK_BYTES / 2;   // one weight image, in halfs
+// pair layout: [nh][chunk][rank = n >> 7][hi,lo][kcore 4][ncore 16][8][8]
+__host__ __device__ __forceinline__ size_t b_img2_off(int nh, int k, int n, int part) {
+  const int c = k >> 5, kk = k & 31, rank = n >> 7, nn = n & 127;
+  return (((((((size_t)(nh * TC_NCHUNK + c) * 2 + rank) * 2 + part) * 4 + (kk >> 3)) * 16 + (nn >> 3)) * 8 + (nn & 7)) * 8) +
+         (kk & 7);
+}
+
 __device__ __forceinline__ void split_f16(float v, float scale, __half& hi, __half& lo) {
   const float s = v * scale;            // power of two: exact
   hi = __float2half_rn(s);
@@ -99,6 +107,10 @@ __global__ void pack_tc_kernel(ic3_policy_params p, __half* __restrict__ img, fl
     const int nh = col >> 8, n = col & 255;
     img[b_img_off(nh, k, n, 0)] = hi;
     img[b_img_off(nh, k, n, 1)] = lo;
+    // second copy for the cta_group::2 kernel: each CTA of a pair owns 128 of the 256 columns
+    __half* img2 = img + B_IMG_HALFS;
+    img2[b_img2_off(nh, k, n, 0)] = hi;
+    img2[b_img2_off(nh, k, n, 1)] = lo;
   }
   if (idx < 4 * H) {
     const int u = idx >> 2, g = idx & 3, row = g * H + u;
@@ -320,18 +332,22 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
 // Bounded wait: a mis-programmed pipeline must never hang the GPU; it raises the flag instead.
+__device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(done)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return done != 0;
+}
 __device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity, int32_t* err) {
-  for (uint32_t spin = 0; spin < WATCHDOG_SPINS; ++spin) {
-    uint32_t done;
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(done)
-        : "r"(bar), "r"(parity)
-        : "memory");
-    if (done) return true;
-  }
+  if (mbar_try(bar, parity)) return true;       // common case in the steady state: already complete
+#pragma unroll 1
+  for (uint32_t spin = 0; spin < WATCHDOG_SPINS; ++spin)
+    if (mbar_try(bar, parity)) return true;
   if (err) atomicOr(err, 0x100);
   return false;
 }
@@ -357,6 +373,15 @@ __device__ __forceinline__ uint32_t cluster_ctarank() {
   asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
   return r;
 }
+// arrive on the mbarrier at the same shared-memory offset of CTA `cta` of this cluster
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t bar, uint32_t cta) {
+  asm volatile(
+      "{\n\t.reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}" ::"r"(bar),
+      "r"(cta)
+      : "memory");
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
@@ -367,6 +392,21 @@ __device__ __forceinline__ void tc_commit_mc(uint32_t bar, uint16_t mask) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
                "h"(mask)
                : "memory");
+}
+// 2-SM forms: the MMA spans the TMEM / shared memory of both CTAs of a pair (M = 256), issued by the leader
+__device__ __forceinline__ void tc_commit2_mc(uint32_t bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+               "h"(mask)
+               : "memory");
+}
+__device__ __forceinline__ void tc_mma2_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
 }
 // D[tmem] (+)= A[smem] . B[smem]^T, kind::f16 (fp16 inputs, fp32 accumulate), one CTA
 __device__ __forceinline__ void tc_mma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
@@ -401,12 +441,86 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 
-// Gate non-linearities on the SFU: ex2.approx (2^-22 rel.) + rcp.approx (1 ulp); both well inside
-// the 1e-5 budget of the hidden state (tests/test_gpu_policy.py, tests/test_gpu_rollout.py).
-__device__ __forceinline__ float sigmoid_fast(float v) { return __fdividef(1.f, 1.f + __expf(-v)); }
-__device__ __forceinline__ float tanh_fast(float v) {
-  const float e = __expf(-2.f * fabsf(v));                 // in (0, 1]: no overflow
-  return copysignf(__fdividef(1.f - e, 1.f + e), v);
+// Gate non-linearities on the SFU, one ex2.approx (2^-22 rel.) + one rcp.approx (1 ulp) each, well inside the
+// 1e-5 budget of the hidden state (tests/test_gpu_policy.py, tests/test_gpu_rollout.py).  The epilogue is the
+// pacing stage of the kernel, so the forms are chosen for instruction count: the argument arrives already scaled
+// by -log2(e) (folded into the accumulator scale and the shared-memory bias copy), and both functions are
+// 1 / (1 + 2^t), see lstm_cell4.
+__device__ __forceinline__ float ex2_fast(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float rcp_fast(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+constexpr float LOG2E = 1.4426950408889634f;
+
+#ifdef IC3_TC_EXP_TRACE
+// Profiling experiment only (profiles/microbench/trace_lstm.py): CTA 0 timestamps its pipeline roles with
+// %globaltimer so that the overlap of operand stream, MMAs and epilogue can be read off directly.
+__device__ unsigned long long g_tc_trace[4][512];
+__device__ __forceinline__ void tc_trace(int role, int& idx) {
+  if (blockIdx.x == 0 && idx < 512) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    g_tc_trace[role][idx++] = t;
+  }
+}
+#define TC_TRACE(role, idx) tc_trace(role, idx)
+#else
+#define TC_TRACE(role, idx)
+#endif
+// Gate biases pre-multiplied like the accumulator scale: (i, f, o) * -log2(e), g * -2 log2(e); [4H] in shared memory.
+__device__ __forceinline__ void load_scaled_bias(float* s_bias, const float* __restrict__ bias_cat) {
+  for (int idx = threadIdx.x; idx < 4 * TC_H; idx += blockDim.x)
+    s_bias[idx] = __ldg(bias_cat + idx) * ((idx & 3) == 2 ? -2.f * LOG2E : -LOG2E);
+}
+
+// LSTM cell of 4 hidden units from 16 accumulator columns (column 4*u+gate): LSTMCell semantics of comm.py:194.
+// The SFU (16 lanes/clk/SM) is the scarcest pipe of the epilogue, so reciprocals are shared: the four gates of a
+// unit are 1/(1+2^t) with ONE rcp of the product of the four denominators (each 1/a recovered with FMA-pipe
+// multiplies), and the four tanh(c') of the group share one more -- 6.25 SFU ops per hidden unit instead of 10.
+// Exponents are clamped at 30 (denominators <= 2^30+1, products <= 2^121: no overflow); the clamp changes a
+// sigmoid by < 1e-9.
+__device__ __forceinline__ void lstm_cell4(const uint32_t (&v)[16], const float (&co)[4], const float* s_bias4,
+                                           float (&cn)[4], float (&hn)[4]) {
+  constexpr float SG = -INV_SCALE * LOG2E;
+#ifdef IC3_TC_EXP_SKIP_MATH   // profiling experiment only (profiles/microbench): epilogue without the SFU work
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    cn[j] = fmaf(__uint_as_float(v[4 * j + 1]), SG, co[j]) + __uint_as_float(v[4 * j]);
+    hn[j] = fmaf(__uint_as_float(v[4 * j + 2]), SG, s_bias4[4 * j]) + __uint_as_float(v[4 * j + 3]);
+  }
+  return;
+#endif
+  constexpr float TMAX = 30.f;
+  float go[4], bc[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float4 b = *reinterpret_cast<const float4*>(s_bias4 + 4 * j);
+    const float ai = 1.f + ex2_fast(fminf(fmaf(__uint_as_float(v[4 * j + 0]), SG, b.x), TMAX));
+    const float af = 1.f + ex2_fast(fminf(fmaf(__uint_as_float(v[4 * j + 1]), SG, b.y), TMAX));
+    const float ag = 1.f + ex2_fast(fminf(fmaf(__uint_as_float(v[4 * j + 2]), 2.f * SG, b.z), TMAX));
+    const float ao = 1.f + ex2_fast(fminf(fmaf(__uint_as_float(v[4 * j + 3]), SG, b.w), TMAX));
+    const float p1 = ai * af, p2 = ag * ao;
+    const float r = rcp_fast(p1 * p2);
+    const float r1 = r * p2, r2 = r * p1;              // 1 / (ai af), 1 / (ag ao)
+    const float gi = r1 * af, gf = r1 * ai;            // sigmoid(i), sigmoid(f)
+    const float gg = fmaf(2.f, r2 * ao, -1.f);         // tanh(g) = 2 sigmoid(2g) - 1
+    go[j] = r2 * ag;                                   // sigmoid(o)
+    cn[j] = fmaf(gf, co[j], gi * gg);
+    bc[j] = 1.f + ex2_fast(fminf(cn[j] * (-2.f * LOG2E), TMAX));
+  }
+  const float q1 = bc[0] * bc[1], q2 = bc[2] * bc[3];
+  const float r = rcp_fast(q1 * q2);
+  const float r1 = r * q2, r2 = r * q1;
+  hn[0] = go[0] * fmaf(2.f, r1 * bc[1], -1.f);         // o * tanh(c')
+  hn[1] = go[1] * fmaf(2.f, r1 * bc[0], -1.f);
+  hn[2] = go[2] * fmaf(2.f, r2 * bc[3], -1.f);
+  hn[3] = go[3] * fmaf(2.f, r2 * bc[2], -1.f);
 }
 
 // ---- the tensor-core kernel -----------------------------------------------------------------------
@@ -425,6 +539,130 @@ constexpr int EPI_THREADS = EPI_WARPS * 32;
 constexpr int TC_P_THREADS = EPI_THREADS + 64;   // + producer warp + MMA warp
 constexpr int NSLOT = 8;             // partial-logit slots per row: (column half of the item) x (column quarter of the warp)
 
+// Two adjacent lanes (rows 2k, 2k+1 of the tile) hold 8 consecutive floats of their own row each (a = first 4,
+// b = last 4).  Written directly, every STG.128 of the warp touches 32 half-used 32-byte sectors; after one
+// exchange the pair writes row 2k with one instruction and row 2k+1 with the next, 32 contiguous bytes each, so
+// L2 sees whole sectors (half the write transactions; the kernel is paced by L2 transactions).
+__device__ __forceinline__ void pair_store8(float* pe, float* po, const float (&a)[4], const float (&b)[4], bool ev, bool ov,
+                                            bool odd) {
+  float r[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) r[j] = __shfl_xor_sync(IC3_FULL_MASK, odd ? a[j] : b[j], 1);
+  const float4 x1 = odd ? make_float4(r[0], r[1], r[2], r[3]) : make_float4(a[0], a[1], a[2], a[3]);
+  const float4 x2 = odd ? make_float4(b[0], b[1], b[2], b[3]) : make_float4(r[0], r[1], r[2], r[3]);
+#ifdef IC3_TC_EXP_SKIP_STORE   // profiling experiment only: keep the values live, store (almost) nothing
+  ev = ev && (x1.x + x1.y + x1.z + x1.w == 12345.678f);
+  ov = ov && (x2.x + x2.y + x2.z + x2.w == 12345.678f);
+#endif
+  if (ev) *reinterpret_cast<float4*>(pe + (odd ? 4 : 0)) = x1;
+  if (ov) *reinterpret_cast<float4*>(po + (odd ? 4 : 0)) = x2;
+}
+
+// One work item of an epilogue thread = (row of the tile, 16 hidden units): LSTM cell from the finished
+// accumulator, h'/c' stores, partial head logits.  `remote_release`: the accumulator barrier lives in the
+// leader CTA of the pair (cta_group::2 kernel).
+// Previous cell state of an epilogue thread's 16 hidden units (zero for a fresh episode).  Independent of the
+// MMAs, so the caller issues it before waiting for the accumulator.  (Prefetching it one whole item ahead was
+// measured: no gain -- the load is not on the critical path -- and the 16 extra live registers cost 4%.)
+__device__ __forceinline__ void load_cold(const ic3_policy_cfg& cfg, const ic3_policy_io& io, int tile, int nh, int quarter,
+                                          int cq, int lane, float4 (&cold)[4]) {
+  const int R = cfg.B * cfg.N;
+  const int row = tile * TC_M + quarter * 32 + lane;
+  const bool inrange = row < R;
+  bool fr = false;
+  if (inrange && io.fresh) fr = io.fresh[row / cfg.N] != 0;
+  const int ubase = nh * (TC_NH / 4) + cq * 16;
+#pragma unroll
+  for (int cg = 0; cg < 4; ++cg) {
+    cold[cg] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (inrange && !fr) cold[cg] = *reinterpret_cast<const float4*>(io.c + (size_t)row * TC_H + ubase + cg * 4);
+  }
+}
+
+__device__ __forceinline__ void epilogue_item(const ic3_policy_cfg& cfg, const ic3_policy_io& io, const float* s_bias,
+                                              const float* s_hw, float* __restrict__ partial, uint32_t tmem_base,
+                                              uint32_t bar_tfull, uint32_t bar_tempty, uint32_t li, int tile, int nh,
+                                              int quarter, int cq, int lane, const float4 (&cold)[4], bool& ok,
+                                              bool remote_release) {
+  const uint32_t acc = li & 1;
+  const int R = cfg.B * cfg.N;
+  const int row = tile * TC_M + quarter * 32 + lane;       // row parity == lane parity
+  const bool odd = lane & 1;
+  const bool inrange = row < R;
+  const int ubase = nh * (TC_NH / 4) + cq * 16;
+#ifdef IC3_TC_EXP_TRACE
+  int tr = 4 * (int)li;
+  const bool tracer = quarter == 0 && cq == 0 && lane == 0;
+  if (tracer) TC_TRACE(2, tr);
+#endif
+  if (ok) ok = mbar_wait(bar_tfull + 8 * acc, (li >> 1) & 1, io.err);
+  tc_fence_after();
+#ifdef IC3_TC_EXP_TRACE
+  if (tracer) TC_TRACE(2, tr);
+#endif
+#ifdef IC3_TC_EXP_SKIP_EPI   // profiling experiment only: the epilogue just hands the accumulator back
+  tc_fence_before();
+  __syncwarp();
+  if (lane == 0) {
+    if (!remote_release) mbar_arrive(bar_tempty + 8 * acc);
+    else mbar_arrive_remote(bar_tempty + 8 * acc, 0);
+  }
+  if (cold[0].x == 12345.678f && partial) partial[row] = cold[1].y + cold[2].z + cold[3].w + s_bias[ubase] + s_hw[odd];
+  return;
+#endif
+  const bool valid = ok && inrange;
+  const int erow = row & ~1, orow = row | 1;
+  const bool ev = ok && erow < R, ov = ok && orow < R;     // validity of the two rows this lane pair writes
+  const uint32_t taddr = tmem_base + acc * TC_NH + cq * 64 + ((uint32_t)(quarter * 32) << 16);
+  float part[HEAD_PAD];
+#pragma unroll
+  for (int o = 0; o < HEAD_PAD; ++o) part[o] = 0.f;
+#pragma unroll
+  for (int cp = 0; cp < 2; ++cp) {          // 8 hidden units (32 accumulator columns) at a time
+    uint32_t v0[16], v1[16];
+    tmem_ld16(taddr + cp * 32, v0);
+    tmem_ld16(taddr + cp * 32 + 16, v1);
+    const int u0 = ubase + cp * 8;
+    float cn0[4] = {0.f, 0.f, 0.f, 0.f}, hn0[4] = {0.f, 0.f, 0.f, 0.f};
+    float cn1[4] = {0.f, 0.f, 0.f, 0.f}, hn1[4] = {0.f, 0.f, 0.f, 0.f};
+    if (valid) {
+      const float co0[4] = {cold[2 * cp].x, cold[2 * cp].y, cold[2 * cp].z, cold[2 * cp].w};
+      const float co1[4] = {cold[2 * cp + 1].x, cold[2 * cp + 1].y, cold[2 * cp + 1].z, cold[2 * cp + 1].w};
+      lstm_cell4(v0, co0, s_bias + 4 * u0, cn0, hn0);
+      lstm_cell4(v1, co1, s_bias + 4 * (u0 + 4), cn1, hn1);
+      if (partial) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float hv = j < 4 ? hn0[j & 3] : hn1[j & 3];
+          const float4 w0 = *reinterpret_cast<const float4*>(&s_hw[(u0 + j) * HEAD_PAD]);
+          const float4 w1 = *reinterpret_cast<const float4*>(&s_hw[(u0 + j) * HEAD_PAD + 4]);
+          part[0] = fmaf(hv, w0.x, part[0]); part[1] = fmaf(hv, w0.y, part[1]);
+          part[2] = fmaf(hv, w0.z, part[2]); part[3] = fmaf(hv, w0.w, part[3]);
+          part[4] = fmaf(hv, w1.x, part[4]); part[5] = fmaf(hv, w1.y, part[5]);
+          part[6] = fmaf(hv, w1.z, part[6]); part[7] = fmaf(hv, w1.w, part[7]);
+        }
+      }
+    }
+    pair_store8(io.c_out + (size_t)erow * TC_H + u0, io.c_out + (size_t)orow * TC_H + u0, cn0, cn1, ev, ov, odd);
+    pair_store8(io.h_out + (size_t)erow * TC_H + u0, io.h_out + (size_t)orow * TC_H + u0, hn0, hn1, ev, ov, odd);
+  }
+  tc_fence_before();
+#ifdef IC3_TC_EXP_TRACE
+  if (tracer) TC_TRACE(2, tr);
+#endif
+  __syncwarp();                              // every lane of the warp is done reading the accumulator:
+  if (lane == 0) {                           // one arrival per warp (remote arrivals on one barrier serialise)
+    if (!remote_release) mbar_arrive(bar_tempty + 8 * acc);
+    else mbar_arrive_remote(bar_tempty + 8 * acc, 0);        // ... on the leader's barrier
+  }
+  if (partial) {                             // slot = (column half of the item, column quarter of the warp)
+    const size_t so = (size_t)(nh * 4 + cq) * HEAD_PAD;
+    const float pa[4] = {part[0], part[1], part[2], part[3]}, pb[4] = {part[4], part[5], part[6], part[7]};
+    pair_store8(partial + (size_t)erow * NSLOT * HEAD_PAD + so, partial + (size_t)orow * NSLOT * HEAD_PAD + so, pa, pb, ev,
+                ov, odd);
+  }
+}
+
 // CL = thread-block cluster size.  The CL CTAs of a cluster work on CL consecutive row tiles and the SAME
 // column half, so they consume identical weight (B) chunks: each CTA fetches 1/CL of every chunk and multicasts
 // it to all peers; a stage is recycled when the MMAs of ALL peers have released it (multicast commit).
@@ -441,6 +679,8 @@ __global__ void __launch_bounds__(TC_P_THREADS, 1) lstm_tc_kernel(ic3_policy_cfg
   // head weights, unit-major [128][8] (zero padded): the epilogue folds value/action-head dot products
   // of its 32 hidden units into per-slot partial logits (partial != nullptr  <=>  nout <= 8)
   float* s_hw = reinterpret_cast<float*>(smem + NSTAGE_P * STAGE_BYTES + 256);
+  float* s_bias = s_hw + TC_H * HEAD_PAD;
+  load_scaled_bias(s_bias, bias_cat);
   if (partial) {
     for (int idx = threadIdx.x; idx < TC_H * HEAD_PAD; idx += blockDim.x) {
       const int u = idx / HEAD_PAD, o = idx - u * HEAD_PAD;
@@ -461,7 +701,7 @@ __global__ void __launch_bounds__(TC_P_THREADS, 1) lstm_tc_kernel(ic3_policy_cfg
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(bar_tfull + 8 * a, 1);
-      mbar_init(bar_tempty + 8 * a, EPI_THREADS);
+      mbar_init(bar_tempty + 8 * a, EPI_WARPS);         // one arrival per epilogue warp
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -478,16 +718,28 @@ __global__ void __launch_bounds__(TC_P_THREADS, 1) lstm_tc_kernel(ic3_policy_cfg
 
   if (warp == EPI_WARPS && lane == 0) {
     // ===== producer =====
-    uint32_t g = 0;
+    static_assert(TC_NCHUNK % NSTAGE_P == 0, "stage index must be a function of the chunk index alone");
+    uint32_t li = 0;
     bool ok = true;
-    for (int item = cl; item < nitems && ok; item += ncl) {
+    [[maybe_unused]] int tr = 0;
+    const uint32_t smem_base = smem_u32(smem);
+    for (int item = cl; item < nitems && ok; item += ncl, ++li) {
       const int tile = (item >> 1) * CL + rank, nh = item & 1;
       const unsigned char* a_src = reinterpret_cast<const unsigned char*>(a_img) + (size_t)tile * TC_NCHUNK * A_CHUNK_BYTES;
       const unsigned char* b_src = reinterpret_cast<const unsigned char*>(b_img) + (size_t)nh * TC_NCHUNK * B_CHUNK_BYTES;
-      for (int c = 0; c < TC_NCHUNK && ok; ++c, ++g) {
-        const uint32_t s = g % NSTAGE_P;
-        ok = mbar_wait(bar_empty + 8 * s, ((g / NSTAGE_P) & 1) ^ 1, io.err);
-        const uint32_t dst = smem_u32(smem + s * STAGE_BYTES);
+      // TC_NCHUNK is a multiple of the ring depth: chunk c of every item uses stage c % NSTAGE_P, so the stage
+      // index (and with it every shared-memory address / descriptor below) is a compile-time constant
+#pragma unroll
+      for (int c = 0; c < TC_NCHUNK; ++c) {
+        if (!ok) break;
+        const uint32_t s = c % NSTAGE_P;
+        ok = mbar_wait(bar_empty + 8 * s, ((li * (TC_NCHUNK / NSTAGE_P) + c / NSTAGE_P) & 1) ^ 1, io.err);
+        if (c == 0 || c == TC_NCHUNK - 1) TC_TRACE(0, tr);
+        const uint32_t dst = smem_base + s * STAGE_BYTES;
+#ifdef IC3_TC_EXP_SKIP_TMA   // profiling experiment only: pipeline without the operand stream
+        mbar_arrive(bar_full + 8 * s);
+        continue;
+#endif
         mbar_expect_tx(bar_full + 8 * s, STAGE_BYTES);
         bulk_g2s(dst, a_src + (size_t)c * A_CHUNK_BYTES, A_CHUNK_BYTES, bar_full + 8 * s);
         if (CL == 1) {
@@ -503,28 +755,36 @@ __global__ void __launch_bounds__(TC_P_THREADS, 1) lstm_tc_kernel(ic3_policy_cfg
     // ===== MMA issuer =====
     // instruction descriptor: D = f32 (bits 4-5 = 1), A = B = f16 (0), K-major both, N >> 3 at 17, M >> 4 at 24
     const uint32_t idesc = (1u << 4) | ((uint32_t)(TC_NH >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
-    uint32_t g = 0, li = 0;
+    uint32_t li = 0;
     bool ok = true;
+    [[maybe_unused]] int tr = 0;
+    // descriptors of stage 0 / k-step 0; every other one is + (byte offset >> 4) in the address field.
+    // A: kcore block = 16 rcores x 128 B = 2048 B; B: 32 ncores x 128 B = 4096 B; lo half follows hi half
+    const uint64_t dA = make_desc(smem_u32(smem), 2048, 128), dB = make_desc(smem_u32(smem) + A_CHUNK_BYTES, 4096, 128);
     for (int item = cl; item < nitems && ok; item += ncl, ++li) {
       const uint32_t acc = li & 1;
       ok = mbar_wait(bar_tempty + 8 * acc, ((li >> 1) & 1) ^ 1, io.err);   // epilogue drained this accumulator
       tc_fence_after();
+      TC_TRACE(1, tr);
       const uint32_t tmem_d = tmem_base + acc * TC_NH;
-      for (int c = 0; c < TC_NCHUNK && ok; ++c, ++g) {
-        const uint32_t s = g % NSTAGE_P;
-        ok = mbar_wait(bar_full + 8 * s, (g / NSTAGE_P) & 1, io.err);
+#pragma unroll
+      for (int c = 0; c < TC_NCHUNK; ++c) {
+        if (!ok) break;
+        const uint32_t s = c % NSTAGE_P;
+        ok = mbar_wait(bar_full + 8 * s, (li * (TC_NCHUNK / NSTAGE_P) + c / NSTAGE_P) & 1, io.err);
         tc_fence_after();
-        const uint32_t a0 = smem_u32(smem + s * STAGE_BYTES), b0 = a0 + A_CHUNK_BYTES;
+        if (c == 0 || c == TC_NCHUNK - 1) TC_TRACE(1, tr);
 #pragma unroll
         for (int ks = 0; ks < TC_KC / 16; ++ks) {
-          // A: kcore block = 16 rcores x 128 B = 2048 B; B: 32 ncores x 128 B = 4096 B; lo half follows hi half
-          const uint64_t da_hi = make_desc(a0 + ks * 4096, 2048, 128);
-          const uint64_t da_lo = make_desc(a0 + A_CHUNK_BYTES / 2 + ks * 4096, 2048, 128);
-          const uint64_t db_hi = make_desc(b0 + ks * 8192, 4096, 128);
-          const uint64_t db_lo = make_desc(b0 + B_CHUNK_BYTES / 2 + ks * 8192, 4096, 128);
+          const uint64_t da_hi = dA + ((s * STAGE_BYTES + ks * 4096) >> 4);
+          const uint64_t da_lo = dA + ((s * STAGE_BYTES + A_CHUNK_BYTES / 2 + ks * 4096) >> 4);
+          const uint64_t db_hi = dB + ((s * STAGE_BYTES + ks * 8192) >> 4);
+          const uint64_t db_lo = dB + ((s * STAGE_BYTES + B_CHUNK_BYTES / 2 + ks * 8192) >> 4);
+#ifndef IC3_TC_EXP_SKIP_MMA   // profiling experiment only: pipeline without the tensor work
           tc_mma_f16(tmem_d, da_hi, db_hi, idesc, (c | ks) != 0);
           tc_mma_f16(tmem_d, da_lo, db_hi, idesc, 1);
           tc_mma_f16(tmem_d, da_hi, db_lo, idesc, 1);
+#endif
         }
         if (CL == 1) tc_commit(bar_empty + 8 * s);      // frees the stage when these MMAs have read it
         else tc_commit_mc(bar_empty + 8 * s, CMASK);    // ... in every CTA of the cluster
@@ -534,72 +794,14 @@ __global__ void __launch_bounds__(TC_P_THREADS, 1) lstm_tc_kernel(ic3_policy_cfg
   } else if (warp < EPI_WARPS) {
     // ===== epilogue: thread = (row of the tile, 16 hidden units) =====
     const int quarter = warp & 3, cq = warp >> 2;
-    const int r = quarter * 32 + lane;
-    const int R = cfg.B * cfg.N;
     uint32_t li = 0;
     bool ok = true;
     for (int item = cl; item < nitems; item += ncl, ++li) {
       const int tile = (item >> 1) * CL + rank, nh = item & 1;
-      const uint32_t acc = li & 1;
-      const int row = tile * TC_M + r;
-      const bool inrange = row < R;
-      bool fr = false;
-      if (inrange && io.fresh) fr = io.fresh[row / cfg.N] != 0;
-      const int ubase = nh * (TC_NH / 4) + cq * 16;
-      // previous cell state: independent of the MMAs -> fetch it while they are still running
-      float4 cold[4];
-#pragma unroll
-      for (int cg = 0; cg < 4; ++cg) {
-        cold[cg] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (inrange && !fr) cold[cg] = *reinterpret_cast<const float4*>(io.c + (size_t)row * TC_H + ubase + cg * 4);
-      }
-      if (ok) ok = mbar_wait(bar_tfull + 8 * acc, (li >> 1) & 1, io.err);
-      tc_fence_after();
-      const bool valid = ok && inrange;
-      const uint32_t taddr = tmem_base + acc * TC_NH + cq * 64 + ((uint32_t)(quarter * 32) << 16);
-      float part[HEAD_PAD];
-#pragma unroll
-      for (int o = 0; o < HEAD_PAD; ++o) part[o] = 0.f;
-#pragma unroll
-      for (int cg = 0; cg < 4; ++cg) {
-        uint32_t v[16];
-        tmem_ld16(taddr + cg * 16, v);
-        if (valid) {
-          const int u0 = ubase + cg * 4;
-          float cn[4], hn[4];
-          const float co[4] = {cold[cg].x, cold[cg].y, cold[cg].z, cold[cg].w};
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const float4 b = __ldg(reinterpret_cast<const float4*>(bias_cat) + (u0 + j));
-            const float gi = sigmoid_fast(fmaf(__uint_as_float(v[4 * j + 0]), INV_SCALE, b.x));
-            const float gf = sigmoid_fast(fmaf(__uint_as_float(v[4 * j + 1]), INV_SCALE, b.y));
-            const float gg = tanh_fast(fmaf(__uint_as_float(v[4 * j + 2]), INV_SCALE, b.z));
-            const float go = sigmoid_fast(fmaf(__uint_as_float(v[4 * j + 3]), INV_SCALE, b.w));
-            cn[j] = fmaf(gf, co[j], gi * gg);
-            hn[j] = go * tanh_fast(cn[j]);
-          }
-          *reinterpret_cast<float4*>(io.c_out + (size_t)row * TC_H + u0) = make_float4(cn[0], cn[1], cn[2], cn[3]);
-          *reinterpret_cast<float4*>(io.h_out + (size_t)row * TC_H + u0) = make_float4(hn[0], hn[1], hn[2], hn[3]);
-          if (partial) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const float4 w0 = *reinterpret_cast<const float4*>(&s_hw[(u0 + j) * HEAD_PAD]);
-              const float4 w1 = *reinterpret_cast<const float4*>(&s_hw[(u0 + j) * HEAD_PAD + 4]);
-              part[0] = fmaf(hn[j], w0.x, part[0]); part[1] = fmaf(hn[j], w0.y, part[1]);
-              part[2] = fmaf(hn[j], w0.z, part[2]); part[3] = fmaf(hn[j], w0.w, part[3]);
-              part[4] = fmaf(hn[j], w1.x, part[4]); part[5] = fmaf(hn[j], w1.y, part[5]);
-              part[6] = fmaf(hn[j], w1.z, part[6]); part[7] = fmaf(hn[j], w1.w, part[7]);
-            }
-          }
-        }
-      }
-      tc_fence_before();
-      mbar_arrive(bar_tempty + 8 * acc);   // this thread no longer reads the accumulator
-      if (partial && valid) {              // slot = (column half of the CTA item, column quarter of the warp)
-        float4* dst = reinterpret_cast<float4*>(partial + ((size_t)row * NSLOT + (nh * 4 + cq)) * HEAD_PAD);
-        dst[0] = make_float4(part[0], part[1], part[2], part[3]);
-        dst[1] = make_float4(part[4], part[5], part[6], part[7]);
-      }
+      float4 cold[4];         // issued before the accumulator wait: overlaps the MMAs of this item
+      load_cold(cfg, io, tile, nh, quarter, cq, lane, cold);
+      epilogue_item(cfg, io, s_bias, s_hw, partial, tmem_base, bar_tfull, bar_tempty, li, tile, nh, quarter, cq, lane, cold, ok,
+                    false);
     }
   }
   tc_fence_before();
@@ -690,6 +892,163 @@ __global__ void __launch_bounds__(256) heads_kernel(ic3_policy_cfg cfg, ic3_poli
   }
 }
 
+// cta_group::2 version: a CTA pair (cluster of 2) computes a 256-row x 256-column item with ONE 2-SM MMA stream.
+// Each CTA stages its own 128 A rows (16 KB / chunk) and only HALF of the weight chunk (16 KB instead of 32 KB),
+// so the per-SM operand stream drops by a third and the ring holds 6 stages.  Protocol (as in CUTLASS 2-SM kernels):
+// both CTAs allocate TMEM with cta_group::2; the leader (rank 0) issues tcgen05.mma.cta_group::2 once its own stage
+// AND the peer's stage have landed (the peer relays its mbarrier phase with a remote arrive); stage and accumulator
+// hand-offs are multicast commits; both epilogues release the accumulator on the leader's barrier.
+constexpr int PAIR_STAGE_BYTES = A_CHUNK_BYTES + B_CHUNK_BYTES / 2;   // 32 KB
+constexpr int PAIR_NSTAGE = 6;
+__global__ void __launch_bounds__(TC_P_THREADS, 1) lstm_tc_pair_kernel(ic3_policy_cfg cfg, ic3_policy_io io,
+                                                                 const __half* __restrict__ a_img,
+                                                                 const __half* __restrict__ b_img,
+                                                                 const float* __restrict__ bias_cat, int nitems,
+                                                                 const float* __restrict__ head_w, int nout,
+                                                                 float* __restrict__ partial) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + PAIR_NSTAGE * PAIR_STAGE_BYTES);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 30);
+  // head weights, unit-major [128][8] (zero padded): the epilogue folds value/action-head dot products
+  // of its 32 hidden units into per-slot partial logits (partial != nullptr  <=>  nout <= 8)
+  float* s_hw = reinterpret_cast<float*>(smem + PAIR_NSTAGE * PAIR_STAGE_BYTES + 256);
+  float* s_bias = s_hw + TC_H * HEAD_PAD;
+  load_scaled_bias(s_bias, bias_cat);
+  if (partial) {
+    for (int idx = threadIdx.x; idx < TC_H * HEAD_PAD; idx += blockDim.x) {
+      const int u = idx / HEAD_PAD, o = idx - u * HEAD_PAD;
+      s_hw[idx] = o < nout ? __ldg(head_w + (size_t)o * TC_H + u) : 0.f;
+    }
+  }
+  const uint32_t bar_full = smem_u32(bars), bar_empty = smem_u32(bars + PAIR_NSTAGE);
+  const uint32_t bar_pfull = smem_u32(bars + 2 * PAIR_NSTAGE);      // leader: "the peer's stage has landed"
+  const uint32_t bar_tfull = smem_u32(bars + 3 * PAIR_NSTAGE), bar_tempty = smem_u32(bars + 3 * PAIR_NSTAGE + 2);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr int CL = 2;
+  const int rank = (int)cluster_ctarank();
+  const int cl = blockIdx.x / CL, ncl = gridDim.x / CL;     // this pair / pairs in the grid
+  constexpr uint16_t CMASK = 3;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < PAIR_NSTAGE; ++s) {
+      mbar_init(bar_full + 8 * s, 1);
+      mbar_init(bar_empty + 8 * s, 1);         // the leader's multicast commit arrives once in each CTA
+      mbar_init(bar_pfull + 8 * s, 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(bar_tfull + 8 * a, 1);
+      mbar_init(bar_tempty + 8 * a, 2 * EPI_WARPS);     // one arrival per epilogue warp of both CTAs (leader's barrier)
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == EPI_WARPS) {   // all 512 TMEM columns: two 128-lane x 256-column fp32 accumulators
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                          // the peer's barriers are initialised before any remote arrive / commit
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == EPI_WARPS && lane == 0) {
+    // ===== producer =====
+    static_assert(TC_NCHUNK % PAIR_NSTAGE == 0, "stage index must be a function of the chunk index alone");
+    uint32_t li = 0;
+    bool ok = true;
+    const uint32_t smem_base = smem_u32(smem);
+    for (int item = cl; item < nitems && ok; item += ncl, ++li) {
+      const int tile = (item >> 1) * CL + rank, nh = item & 1;
+      const unsigned char* a_src = reinterpret_cast<const unsigned char*>(a_img) + (size_t)tile * TC_NCHUNK * A_CHUNK_BYTES;
+      // pair image: [nh][chunk][rank][16 KB]
+      const unsigned char* b_src = reinterpret_cast<const unsigned char*>(b_img) + (size_t)nh * TC_NCHUNK * B_CHUNK_BYTES +
+                                   (size_t)rank * (B_CHUNK_BYTES / 2);
+#pragma unroll
+      for (int c = 0; c < TC_NCHUNK; ++c) {       // stage index = c % PAIR_NSTAGE: compile-time constant
+        if (!ok) break;
+        const uint32_t s = c % PAIR_NSTAGE;
+        ok = mbar_wait(bar_empty + 8 * s, ((li * (TC_NCHUNK / PAIR_NSTAGE) + c / PAIR_NSTAGE) & 1) ^ 1, io.err);
+        const uint32_t dst = smem_base + s * PAIR_STAGE_BYTES;
+#ifdef IC3_TC_EXP_SKIP_TMA
+        mbar_arrive(bar_full + 8 * s);
+        continue;
+#endif
+        mbar_expect_tx(bar_full + 8 * s, PAIR_STAGE_BYTES);
+        bulk_g2s(dst, a_src + (size_t)c * A_CHUNK_BYTES, A_CHUNK_BYTES, bar_full + 8 * s);
+        bulk_g2s(dst + A_CHUNK_BYTES, b_src + (size_t)c * B_CHUNK_BYTES, B_CHUNK_BYTES / 2, bar_full + 8 * s);
+      }
+    }
+  } else if (warp == EPI_WARPS + 1 && lane == 0) {
+    // ===== MMA issuer =====
+    // instruction descriptor: D = f32, A = B = f16, K-major both, N = 256, M = 256 over the CTA pair
+    const uint32_t idesc = (1u << 4) | ((uint32_t)(TC_NH >> 3) << 17) | ((uint32_t)((2 * TC_M) >> 4) << 24);
+    uint32_t li = 0;
+    bool ok = true;
+    if (rank != 0) {
+      // peer: relay "my stage has landed" to the leader, chunk by chunk
+      for (int item = cl; item < nitems && ok; item += ncl, ++li) {
+#pragma unroll
+        for (int c = 0; c < TC_NCHUNK; ++c) {
+          if (!ok) break;
+          const uint32_t s = c % PAIR_NSTAGE;
+          ok = mbar_wait(bar_full + 8 * s, (li * (TC_NCHUNK / PAIR_NSTAGE) + c / PAIR_NSTAGE) & 1, io.err);
+          mbar_arrive_remote(bar_pfull + 8 * s, 0);
+        }
+      }
+    }
+    // per CTA: A 128 rows (kcore block 2048 B), B 128 of the 256 columns (kcore block 16 ncores x 128 B = 2048 B)
+    const uint64_t dA = make_desc(smem_u32(smem), 2048, 128), dB = make_desc(smem_u32(smem) + A_CHUNK_BYTES, 2048, 128);
+    for (int item = cl; rank == 0 && item < nitems && ok; item += ncl, ++li) {
+      const uint32_t acc = li & 1;
+      ok = mbar_wait(bar_tempty + 8 * acc, ((li >> 1) & 1) ^ 1, io.err);   // both epilogues drained this accumulator
+      tc_fence_after();
+      const uint32_t tmem_d = tmem_base + acc * TC_NH;
+#pragma unroll
+      for (int c = 0; c < TC_NCHUNK; ++c) {
+        if (!ok) break;
+        const uint32_t s = c % PAIR_NSTAGE;
+        const uint32_t ph = (li * (TC_NCHUNK / PAIR_NSTAGE) + c / PAIR_NSTAGE) & 1;
+        ok = mbar_wait(bar_full + 8 * s, ph, io.err);
+        if (ok) ok = mbar_wait(bar_pfull + 8 * s, ph, io.err);
+        tc_fence_after();
+#pragma unroll
+        for (int ks = 0; ks < TC_KC / 16; ++ks) {
+          const uint64_t da_hi = dA + ((s * PAIR_STAGE_BYTES + ks * 4096) >> 4);
+          const uint64_t da_lo = dA + ((s * PAIR_STAGE_BYTES + A_CHUNK_BYTES / 2 + ks * 4096) >> 4);
+          const uint64_t db_hi = dB + ((s * PAIR_STAGE_BYTES + ks * 4096) >> 4);
+          const uint64_t db_lo = dB + ((s * PAIR_STAGE_BYTES + B_CHUNK_BYTES / 4 + ks * 4096) >> 4);
+#ifndef IC3_TC_EXP_SKIP_MMA
+          tc_mma2_f16(tmem_d, da_hi, db_hi, idesc, (c | ks) != 0);
+          tc_mma2_f16(tmem_d, da_lo, db_hi, idesc, 1);
+          tc_mma2_f16(tmem_d, da_hi, db_lo, idesc, 1);
+#endif
+        }
+        tc_commit2_mc(bar_empty + 8 * s, CMASK);    // frees the stage in both CTAs when these MMAs have read it
+      }
+      tc_commit2_mc(bar_tfull + 8 * acc, CMASK);    // accumulator complete, in both CTAs
+    }
+  } else if (warp < EPI_WARPS) {
+    // ===== epilogue: thread = (row of the tile, 16 hidden units) =====
+    const int quarter = warp & 3, cq = warp >> 2;
+    uint32_t li = 0;
+    bool ok = true;
+    for (int item = cl; item < nitems; item += ncl, ++li) {
+      const int tile = (item >> 1) * CL + rank, nh = item & 1;
+      float4 cold[4];         // issued before the accumulator wait: overlaps the MMAs of this item
+      load_cold(cfg, io, tile, nh, quarter, cq, lane, cold);
+      epilogue_item(cfg, io, s_bias, s_hw, partial, tmem_base, bar_tfull, bar_tempty, li, tile, nh, quarter, cq, lane, cold, ok,
+                    rank != 0);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                          // the peer may still read this CTA's smem / arrive on its barriers
+  if (warp == EPI_WARPS) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+  }
+}
+
 // Finish the heads from the NSLOT per-slot partial logits (fixed summation order -> deterministic):
 // value, log-softmax per head, inverse-CDF sampling.  One thread per agent row.
 __global__ void __launch_bounds__(128) heads_finish_kernel(ic3_policy_cfg cfg, ic3_policy_packed w, ic3_policy_io io,
@@ -770,6 +1129,50 @@ static int tc_cluster_size() {
 }
 constexpr int TC_TILE_PAD = 8;   // tiles are padded to whole clusters of up to 8
 
+// IC3_TC_PAIR=1 selects the cta_group::2 kernel (one 2-SM MMA stream per CTA pair); experimental, default off.
+static bool tc_pair_mode() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("IC3_TC_PAIR");
+    v = (e && atoi(e) != 0) ? 1 : 0;
+  }
+  return v == 1;
+}
+
+static int launch_lstm_pair(const ic3_policy_cfg* cfg, const ic3_policy_io* io, const ic3_policy_packed* w,
+                            const __half* a_img, int ntiles_pad, int nout, float* partial, cudaStream_t s) {
+  static int max_clusters = 0;
+  const size_t smem = PAIR_NSTAGE * PAIR_STAGE_BYTES + 256 + TC_H * HEAD_PAD * sizeof(float) + 4 * TC_H * sizeof(float);
+  auto kern = lstm_tc_pair_kernel;
+  cudaLaunchAttribute la[1];
+  la[0].id = cudaLaunchAttributeClusterDimension;
+  la[0].val.clusterDim.x = 2; la[0].val.clusterDim.y = 1; la[0].val.clusterDim.z = 1;
+  if (max_clusters == 0) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    cudaLaunchConfig_t q{};
+    q.gridDim = dim3(2 * 148);
+    q.blockDim = dim3(TC_P_THREADS);
+    q.dynamicSmemBytes = smem;
+    q.attrs = la; q.numAttrs = 1;
+    e = cudaOccupancyMaxActiveClusters(&max_clusters, kern, &q);
+    if (e != cudaSuccess || max_clusters <= 0) return e != cudaSuccess ? (int)e : IC3_E_RANGE;
+  }
+  const int nitems = 2 * (ntiles_pad / 2);                         // (tile pair, column half)
+  const int nclusters = nitems < max_clusters ? nitems : max_clusters;
+  cudaLaunchConfig_t lc{};
+  lc.gridDim = dim3(nclusters * 2);
+  lc.blockDim = dim3(TC_P_THREADS);
+  lc.dynamicSmemBytes = smem;
+  lc.stream = s;
+  lc.attrs = la; lc.numAttrs = 1;
+  const __half* b_img = reinterpret_cast<const __half*>(w->lstm_img) + B_IMG_HALFS;   // the pair-layout copy
+  cudaError_t e = cudaLaunchKernelEx(&lc, kern, *cfg, *io, a_img, b_img, (const float*)w->bias_cat, nitems,
+                                     (const float*)w->head_w, nout, partial);
+  ++g_ic3_launches;
+  return e == cudaSuccess ? IC3_OK : (int)e;
+}
+
 template <int CL>
 static int launch_lstm(const ic3_policy_cfg* cfg, const ic3_policy_io* io, const ic3_policy_packed* w, const __half* a_img,
                        int ntiles_pad, size_t smem, int nout, float* partial, cudaStream_t s) {
@@ -803,6 +1206,17 @@ static int launch_lstm(const ic3_policy_cfg* cfg, const ic3_policy_io* io, const
   ++g_ic3_launches;
   return e == cudaSuccess ? IC3_OK : (int)e;
 }
+
+#ifdef IC3_TC_EXP_TRACE
+extern "C" int ic3_debug_tc_trace(unsigned long long* host) {      // experiment builds only; not part of the C ABI
+  cudaDeviceSynchronize();
+  return (int)cudaMemcpyFromSymbol(host, g_tc_trace, sizeof(unsigned long long) * 4 * 512);
+}
+extern "C" int ic3_debug_tc_trace_clear() {
+  static unsigned long long z[4 * 512];
+  return (int)cudaMemcpyToSymbol(g_tc_trace, z, sizeof(z));
+}
+#endif
 
 uint64_t ic3_tc_workspace_bytes(const ic3_policy_cfg* cfg) {
   if (!cfg || cfg->H != TC_H) return 0;
@@ -868,7 +1282,7 @@ int ic3_tc_policy_step(const ic3_policy_cfg* cfg, const ic3_policy_packed* w, co
     return IC3_E_NULL;
   }
   IC3_LAUNCH_CHECK();
-  const size_t smem = NSTAGE_P * STAGE_BYTES + 256 + TC_H * HEAD_PAD * sizeof(float);
+  const size_t smem = NSTAGE_P * STAGE_BYTES + 256 + TC_H * HEAD_PAD * sizeof(float) + 4 * TC_H * sizeof(float);
   int nout = 1;
   for (int k = 0; k < cfg->nheads; ++k) nout += cfg->head_dim[k];
   const bool fused_heads = nout <= HEAD_PAD;
@@ -876,7 +1290,8 @@ int ic3_tc_policy_step(const ic3_policy_cfg* cfg, const ic3_policy_packed* w, co
                                                            (size_t)ntiles_pad * TC_NCHUNK * A_CHUNK_BYTES)
                                : nullptr;
   int rc = IC3_E_RANGE;
-  switch (tc_cluster_size()) {
+  if (tc_pair_mode()) rc = launch_lstm_pair(cfg, io, w, img, ntiles_pad, nout, partial, s);
+  else switch (tc_cluster_size()) {
     case 1: rc = launch_lstm<1>(cfg, io, w, img, ntiles_pad, smem, nout, partial, s); break;
     case 2: rc = launch_lstm<2>(cfg, io, w, img, ntiles_pad, smem, nout, partial, s); break;
     case 4: rc = launch_lstm<4>(cfg, io, w, img, ntiles_pad, smem, nout, partial, s); break;

@@ -212,13 +212,15 @@ typedef struct {
   float* head_b;   /* [1+sum(na)] */
   /* tcgen05 path (H == 128 only; both NULL selects the fp32 SIMT kernel):
    * lstm_img: fp16 hi/lo split of 256 * [W_ih ; W_ih.C ; W_hh] (K = 384) as ready-made
-   *   shared-memory images, [2 column halves][12 K-chunks][hi,lo][core-matrix layout] = 786432 bytes;
+   *   shared-memory images, [2 column halves][12 K-chunks][hi,lo][core-matrix layout] = 786432 bytes,
+   *   followed by a second copy of the same values in the layout of the 2-SM (cta_group::2) kernel,
+   *   [2 column halves][12 K-chunks][2 CTA ranks][hi,lo][core-matrix layout];
    * bias_cat: [4H] b_ih + b_hh + W_ih.c_b, column 4*u+gate. */
   void* lstm_img;
   float* bias_cat;
 } ic3_policy_packed;
 
-#define IC3_LSTM_IMG_BYTES 786432
+#define IC3_LSTM_IMG_BYTES 1572864
 
 int ic3_policy_pack(const ic3_policy_cfg* cfg, const ic3_policy_params* p,
                     const ic3_policy_packed* out, void* stream);
