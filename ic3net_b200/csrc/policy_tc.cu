@@ -957,6 +957,7 @@ __global__ void __launch_bounds__(TC_P_THREADS, 1) lstm_tc_pair_kernel(ic3_polic
     static_assert(TC_NCHUNK % PAIR_NSTAGE == 0, "stage index must be a function of the chunk index alone");
     uint32_t li = 0;
     bool ok = true;
+    [[maybe_unused]] int tr = 0;
     const uint32_t smem_base = smem_u32(smem);
     for (int item = cl; item < nitems && ok; item += ncl, ++li) {
       const int tile = (item >> 1) * CL + rank, nh = item & 1;
@@ -969,6 +970,7 @@ __global__ void __launch_bounds__(TC_P_THREADS, 1) lstm_tc_pair_kernel(ic3_polic
         if (!ok) break;
         const uint32_t s = c % PAIR_NSTAGE;
         ok = mbar_wait(bar_empty + 8 * s, ((li * (TC_NCHUNK / PAIR_NSTAGE) + c / PAIR_NSTAGE) & 1) ^ 1, io.err);
+        if (c == 0 || c == TC_NCHUNK - 1) TC_TRACE(0, tr);
         const uint32_t dst = smem_base + s * PAIR_STAGE_BYTES;
 #ifdef IC3_TC_EXP_SKIP_TMA
         mbar_arrive(bar_full + 8 * s);
@@ -997,12 +999,14 @@ __global__ void __launch_bounds__(TC_P_THREADS, 1) lstm_tc_pair_kernel(ic3_polic
         }
       }
     }
+    [[maybe_unused]] int tr = 0, tr3 = 0;
     // per CTA: A 128 rows (kcore block 2048 B), B 128 of the 256 columns (kcore block 16 ncores x 128 B = 2048 B)
     const uint64_t dA = make_desc(smem_u32(smem), 2048, 128), dB = make_desc(smem_u32(smem) + A_CHUNK_BYTES, 2048, 128);
     for (int item = cl; rank == 0 && item < nitems && ok; item += ncl, ++li) {
       const uint32_t acc = li & 1;
       ok = mbar_wait(bar_tempty + 8 * acc, ((li >> 1) & 1) ^ 1, io.err);   // both epilogues drained this accumulator
       tc_fence_after();
+      TC_TRACE(1, tr);
       const uint32_t tmem_d = tmem_base + acc * TC_NH;
 #pragma unroll
       for (int c = 0; c < TC_NCHUNK; ++c) {
@@ -1010,8 +1014,10 @@ __global__ void __launch_bounds__(TC_P_THREADS, 1) lstm_tc_pair_kernel(ic3_polic
         const uint32_t s = c % PAIR_NSTAGE;
         const uint32_t ph = (li * (TC_NCHUNK / PAIR_NSTAGE) + c / PAIR_NSTAGE) & 1;
         ok = mbar_wait(bar_full + 8 * s, ph, io.err);
+        if (c == 0 || c == TC_NCHUNK - 1) TC_TRACE(3, tr3);          // own stage landed
         if (ok) ok = mbar_wait(bar_pfull + 8 * s, ph, io.err);
         tc_fence_after();
+        if (c == 0 || c == TC_NCHUNK - 1) TC_TRACE(1, tr);           // ... and the peer's
 #pragma unroll
         for (int ks = 0; ks < TC_KC / 16; ++ks) {
           const uint64_t da_hi = dA + ((s * PAIR_STAGE_BYTES + ks * 4096) >> 4);

@@ -48,4 +48,5 @@ for i in range(10):
     e = t[2, 4 * i:4 * i + 3]
     if not m.any():
         break
-    print("%2d | %7.2f %7.2f | %7.2f %7.2f %7.2f | %7.2f %7.2f %7.2f" % ((i,) + tuple(us(v) for v in list(p) + list(m) + list(e))))
+    print("%2d | %7.2f %7.2f | %7.2f %7.2f %7.2f | %7.2f %7.2f %7.2f" % ((i,) + tuple(us(v) for v in list(p) + list(m) + list(e))),
+          "| own stage landed (pair kernel): %7.2f %7.2f" % tuple(us(v) for v in t[3, 2 * i:2 * i + 2]) if t[3].any() else "")
