@@ -89,6 +89,16 @@ class MultiGPUTrainer(object):
     def reduce(self, stat):
         """Sum gradients and additive stats over ranks; returns the merged stat."""
         params = self.trainer.params
+        opt = self.trainer.optimizer
+        if hasattr(opt, 'flat_grads'):
+            # FlatRMSprop: the gradients already live in one buffer -> all-reduce it in place; the division by the
+            # global step count (multi_processing.py:95) is folded into the optimizer kernel (train_batch below)
+            vec, shapes = pack_stat(stat, opt.flat_grads.device)
+            if _dist_on():
+                dist.all_reduce(opt.flat_grads, op=dist.ReduceOp.SUM)      # multi_processing.py:92-94
+                self.collectives += 1
+                dist.all_reduce(vec, op=dist.ReduceOp.SUM)                 # multi_processing.py:86-88
+            return unpack_stat(vec, shapes, dict(stat))
         flat, grads = flat_grad_buffer(params)
         dev = flat.device if flat is not None else (params[0].device if params else torch.device('cpu'))
         vec, shapes = pack_stat(stat, dev)
@@ -109,7 +119,10 @@ class MultiGPUTrainer(object):
         s = self.trainer.compute_grad(batch)
         merge_stat(s, stat)
         stat = self.reduce(stat)
-        self.trainer.optimizer.step()                            # multi_processing.py:97
+        if hasattr(self.trainer.optimizer, 'flat_grads'):
+            self.trainer.optimizer.step(grad_div=stat['num_steps'])   # multi_processing.py:95-97 in one kernel
+        else:
+            self.trainer.optimizer.step()                        # multi_processing.py:97
         return stat
 
     def state_dict(self):

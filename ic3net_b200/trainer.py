@@ -29,9 +29,9 @@ from collections import namedtuple
 import numpy as np
 import torch
 import torch.nn.functional as F
-from torch import optim
 
 from . import _lib
+from .optim import FlatRMSprop
 from .utils import merge_stat
 
 Transition = namedtuple('Transition', ('state', 'action', 'action_out', 'value', 'episode_mask',
@@ -48,7 +48,8 @@ class Trainer(object):
         self.env = env                       # GymWrapper
         self.display = False
         self.last_step = False
-        self.optimizer = optim.RMSprop(policy_net.parameters(), lr=args.lrate, alpha=0.97, eps=1e-6)
+        # trainer.py:21-22 RMSprop(lr, alpha=0.97, eps=1e-6) as one kernel over flat buffers (optim.py)
+        self.optimizer = FlatRMSprop(policy_net.parameters(), lr=args.lrate, alpha=0.97, eps=1e-6)
         self.params = [p for p in self.policy_net.parameters()]
         self.obs_mode = getattr(args, 'obs_mode', 'index')      # 'index' | 'dense'
         self.use_graph = bool(getattr(args, 'use_graph', False))
@@ -355,10 +356,7 @@ class Trainer(object):
         self.optimizer.zero_grad(set_to_none=False)
         s = self.compute_grad(batch)
         merge_stat(s, stat)
-        for p in self.params:
-            if p._grad is not None:
-                p._grad.data /= stat['num_steps']
-        self.optimizer.step()
+        self.optimizer.step(grad_div=stat['num_steps'])      # grad /= num_steps, then the update (trainer.py:251-254)
         return stat
 
     def state_dict(self):

@@ -276,6 +276,16 @@ int ic3_sample_actions(const ic3_policy_cfg* cfg, const float* logp, const uint3
 int ic3_returns_scan(int32_t T, int32_t B, int32_t N, float gamma, float mean_ratio, const float* reward,
                      const uint8_t* episode_mask, const uint8_t* mini_mask, float* returns, void* stream);
 
+/* ------------------------------------------------------------------------
+ * Optimizer step  (trainer.py:21-22 RMSprop(lr, alpha=0.97, eps=1e-6); trainer.py:251-256 and
+ * multi_processing.py:95-97: summed gradient / global num_steps, then one step)
+ * ---------------------------------------------------------------------- */
+/* All live parameters, their gradients and the RMSprop second-moment state as three flat,
+ * 16-byte aligned float32 buffers of n elements:  g = grad / grad_div (stored back into grad);
+ * square_avg = alpha*square_avg + (1-alpha)*g*g;  param -= lr * g / (sqrt(square_avg) + eps). */
+int ic3_rmsprop_step(int64_t n, float lr, float alpha, float eps, float grad_div, float* grad,
+                     float* param, float* square_avg, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

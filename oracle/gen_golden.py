@@ -538,7 +538,46 @@ def gen_grad_case(name, seed, env_id, wseed, **kw):
     save(name, meta, **arrays)
 
 
+def gen_rmsprop_case(name, seed, nupdates=5, lr=0.001):
+    """torch.optim.RMSprop (the module trainer.py:21-22 instantiates) in float64, driven like
+    Trainer.train_batch (trainer.py:245-256): zero_grad, accumulate, grad /= num_steps, step."""
+    import torch
+    g = torch.Generator().manual_seed(seed)
+    shapes = [(32, 19), (32,), (7, 32), (7,), (1, 32), (1,), (5, 5), (3,)]      # last two: never get a gradient
+    live = [True] * 6 + [False, False]
+    params = [torch.nn.Parameter(torch.randn(*s, generator=g, dtype=torch.float64) * 0.1) for s in shapes]
+    opt = torch.optim.RMSprop(params, lr=lr, alpha=0.97, eps=1e-6)
+    arrays = {}
+    for i, p_ in enumerate(params):
+        arrays["p0_%d" % i] = p_.detach().numpy().copy()
+    steps = []
+    for u in range(nupdates):
+        opt.zero_grad()
+        ns = int(torch.randint(200, 900, (1,), generator=g))
+        steps.append(ns)
+        for i, p_ in enumerate(params):
+            if live[i]:
+                scale = 10.0 ** float(torch.randint(-3, 3, (1,), generator=g))      # wide dynamic range
+                p_.grad = torch.randn(*shapes[i], generator=g, dtype=torch.float64) * scale * ns
+                arrays["g%d_%d" % (u, i)] = p_.grad.numpy().copy()
+        for p_ in params:                                                          # trainer.py:251-253
+            if p_._grad is not None:
+                p_._grad.data /= ns
+        opt.step()
+        for i, p_ in enumerate(params):
+            arrays["p%d_%d" % (u + 1, i)] = p_.detach().numpy().copy()
+    for i, p_ in enumerate(params):
+        if live[i]:
+            arrays["v_%d" % i] = opt.state[p_]["square_avg"].numpy().copy()
+    meta = dict(kind="rmsprop", lr=lr, alpha=0.97, eps=1e-6, nupdates=nupdates, num_steps=steps, live=live,
+                shapes=[list(s) for s in shapes], torch=torch.__version__)
+    save(name, meta, **arrays)
+
+
 def main():
+    if "--rmsprop-only" in sys.argv:          # needs torch only, not the reference checkout
+        gen_rmsprop_case("rmsprop_ref", 81)
+        return 0
     if not ref_shims.reference_available():
         print("reference not available; nothing generated")
         return 1
@@ -599,6 +638,7 @@ def main():
     gen_grad_case("grad_tj_easy_commnet", 64, 0, 74, env_name="traffic_junction", nagents=5, dim=6, vision=0,
                   max_steps=20, hid_size=64, commnet=True, difficulty="easy", add_rate_min=0.3, add_rate_max=0.3,
                   batch_size=50, mean_ratio=0.5, gamma=0.9)
+    gen_rmsprop_case("rmsprop_ref", 81)
     return 0
 
 

@@ -172,3 +172,22 @@ def test_gradient_golden(name):
             assert np.allclose([q.sum(), np.abs(q).sum(), (q ** 2).sum()], ref, rtol=1e-8)
             checked += 1
     assert checked >= 8
+
+
+def test_rmsprop_golden():
+    """oracle/optim.py against torch.optim.RMSprop driven like trainer.py:245-256 (fixture from gen_golden.py)."""
+    from oracle import optim as ooptim
+    meta, z = load_golden("rmsprop_ref")
+    n = len(meta["shapes"])
+    params = [z["p0_%d" % i].copy() for i in range(n)]
+    sq = [np.zeros_like(p) for p in params]
+    for u, ns_ in enumerate(meta["num_steps"]):
+        grads = [z["g%d_%d" % (u, i)] if meta["live"][i] else None for i in range(n)]
+        ooptim.rmsprop_step(params, grads, sq, meta["lr"], meta["alpha"], meta["eps"], grad_div=ns_)
+        for i in range(n):
+            assert np.allclose(params[i], z["p%d_%d" % (u + 1, i)], rtol=1e-12, atol=1e-14), (u, i)
+    for i in range(n):
+        if meta["live"][i]:
+            assert np.allclose(sq[i], z["v_%d" % i], rtol=1e-12, atol=0)
+        else:                                   # never touched: parameter unchanged, no state
+            assert np.array_equal(params[i], z["p0_%d" % i])
