@@ -402,11 +402,12 @@ def per_kernel_times(tr, a, env, net, steps, C, torch, _lib):
 
     ws = net.workspace(B)[0]
     W_ = 2 * e.vision + 1
-    fused_x = tr.obs_mode != "dense" and ws is not None and W_ * W_ <= 25     # index encoder fused into the policy step
+    fused_x = tr._fused_x()                                   # index encoder fused into the policy step
     src = {}
     if fused_x:
         src = dict(tj_env=C.addressof(e.cfg), tj_state=C.addressof(e.state)) if is_tj else \
             dict(pp_env=C.addressof(e.cfg), pp_state=C.addressof(e.state))
+        src["x_table"] = _lib.ptr(tr._encoder_table(cfg, w))  # same path as Trainer._enqueue
     for t in range(steps):
         if tr.obs_mode == "dense":
             if is_tj:

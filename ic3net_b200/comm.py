@@ -72,7 +72,8 @@ class CommNetMLP(nn.Module):
                                comm_avg=int(getattr(args, 'comm_mode', 'avg') == 'avg'),
                                comm_mask_zero=int(bool(args.comm_mask_zero)),
                                env_id0=int(getattr(args, 'env_id0', 0)),
-                               seed=int(getattr(args, 'seed', 0)) & 0xFFFFFFFFFFFFFFFF)
+                               seed=int(getattr(args, 'seed', 0)) & 0xFFFFFFFFFFFFFFFF,
+                               obs_off=0, obs_vocab=0, obs_ncount=0)
         self._packed = None
         self._packed_key = None
         # 'tc' = tcgen05 tensor-core path (csrc/policy_tc.cu, hid_size 128), 'simt' = fp32 CUDA-core kernel
@@ -82,6 +83,12 @@ class CommNetMLP(nn.Module):
         if self.policy_impl == 'tc' and H != 128:
             raise NotImplementedError("the tensor-core policy path is specialised for hid_size 128")
         self._ws = {}
+
+    def set_obs_layout(self, off, vocab, ncount):
+        """Observation layout hint (include/ic3net_b200.h, ic3_policy_cfg.obs_vocab): lets the encoder sum the
+        one-hot class terms separately from the counts, so the class part can come from a per-position table and
+        the dense / index / fused encoders stay bit-identical.  (0, 0, 0) = plain single sum."""
+        self._cfg_proto.update(obs_off=int(off), obs_vocab=int(vocab), obs_ncount=int(ncount))
 
     # ---- kernel-side weights ---------------------------------------------------
     def policy_cfg(self, B):

@@ -295,17 +295,39 @@ __device__ __forceinline__ void store_x(const float (&acc)[CPT], float* __restri
   else xrow[lane] = acc[0];
 }
 
+// Observation layout hint of ic3_policy_cfg (obs_off, obs_vocab, obs_ncount): is feature f a one-hot position
+// class (first accumulator, may come from a per-position table) or a count / scalar (second accumulator)?
+struct ObsLayout {
+  int off, V, ncount;
+  __device__ __forceinline__ bool is_class(int f) const {
+    if (V <= 0) return true;            // no hint: one sum
+    if (f < off) return false;
+    return ((f - off) % V) < V - ncount;
+  }
+};
+
+template <int CPT>
+__device__ __forceinline__ void store_x2(const float (&a)[CPT], const float (&b)[CPT], float* __restrict__ xrow, int lane) {
+  float r[CPT];
+#pragma unroll
+  for (int c = 0; c < CPT; ++c) r[c] = a[c] + b[c];      // x = (bias + class terms) + (other terms)
+  store_x<CPT>(r, xrow, lane);
+}
+
 template <int H, bool VEC>
 __global__ void __launch_bounds__(256) encoder_dense_kernel(const float* __restrict__ obs, const float* __restrict__ wT,
                                                             const float* __restrict__ bias, float* __restrict__ x,
-                                                            int rows, int O) {
+                                                            int rows, int O, ObsLayout lay) {
   constexpr int CPT = H / 32;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int row = blockIdx.x * (blockDim.x >> 5) + warp;
   if (row >= rows) return;
-  float acc[CPT];
+  float acc[CPT], acc2[CPT];
 #pragma unroll
-  for (int c = 0; c < CPT; ++c) acc[c] = __ldg(bias + lane * CPT + c);
+  for (int c = 0; c < CPT; ++c) {
+    acc[c] = __ldg(bias + lane * CPT + c);
+    acc2[c] = 0.f;
+  }
   const float* orow = obs + (size_t)row * O;
   constexpr int U = 4;
   if (VEC) {
@@ -326,11 +348,12 @@ __global__ void __launch_bounds__(256) encoder_dense_kernel(const float* __restr
           m &= m - 1;
           const float sx = __shfl_sync(IC3_FULL_MASK, v[u].x, src), sy = __shfl_sync(IC3_FULL_MASK, v[u].y, src);
           const float sz = __shfl_sync(IC3_FULL_MASK, v[u].z, src), sw = __shfl_sync(IC3_FULL_MASK, v[u].w, src);
-          const float* wr = wT + (size_t)(base + u * 32 + src) * 4 * H;
-          if (sx != 0.f) axpy_row<CPT>(acc, sx, wr, lane);
-          if (sy != 0.f) axpy_row<CPT>(acc, sy, wr + H, lane);
-          if (sz != 0.f) axpy_row<CPT>(acc, sz, wr + 2 * H, lane);
-          if (sw != 0.f) axpy_row<CPT>(acc, sw, wr + 3 * H, lane);
+          const int f0 = (base + u * 32 + src) * 4;
+          const float* wr = wT + (size_t)f0 * H;
+          if (sx != 0.f) { if (lay.is_class(f0)) axpy_row<CPT>(acc, sx, wr, lane); else axpy_row<CPT>(acc2, sx, wr, lane); }
+          if (sy != 0.f) { if (lay.is_class(f0 + 1)) axpy_row<CPT>(acc, sy, wr + H, lane); else axpy_row<CPT>(acc2, sy, wr + H, lane); }
+          if (sz != 0.f) { if (lay.is_class(f0 + 2)) axpy_row<CPT>(acc, sz, wr + 2 * H, lane); else axpy_row<CPT>(acc2, sz, wr + 2 * H, lane); }
+          if (sw != 0.f) { if (lay.is_class(f0 + 3)) axpy_row<CPT>(acc, sw, wr + 3 * H, lane); else axpy_row<CPT>(acc2, sw, wr + 3 * H, lane); }
         }
       }
     }
@@ -349,12 +372,14 @@ __global__ void __launch_bounds__(256) encoder_dense_kernel(const float* __restr
           const int src = __ffs(m) - 1;
           m &= m - 1;
           const float s = __shfl_sync(IC3_FULL_MASK, v[u], src);
-          axpy_row<CPT>(acc, s, wT + (size_t)(base + u * 32 + src) * H, lane);
+          const int f = base + u * 32 + src;
+          if (lay.is_class(f)) axpy_row<CPT>(acc, s, wT + (size_t)f * H, lane);
+          else axpy_row<CPT>(acc2, s, wT + (size_t)f * H, lane);
         }
       }
     }
   }
-  store_x<CPT>(acc, x + (size_t)row * H, lane);
+  store_x2<CPT>(acc, acc2, x + (size_t)row * H, lane);
 }
 
 // ---------------------------------------------------------------------------
@@ -364,7 +389,8 @@ __global__ void __launch_bounds__(256) encoder_dense_kernel(const float* __restr
 template <int H>
 __global__ void __launch_bounds__(256) pp_encoder_index_kernel(ic3_pp_cfg env, ic3_pp_state st,
                                                                const float* __restrict__ wT,
-                                                               const float* __restrict__ bias, float* __restrict__ x) {
+                                                               const float* __restrict__ bias, float* __restrict__ x,
+                                                               bool split) {
   constexpr int CPT = H / 32;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int row = blockIdx.x * (blockDim.x >> 5) + warp;
@@ -378,9 +404,12 @@ __global__ void __launch_bounds__(256) pp_encoder_index_kernel(ic3_pp_cfg env, i
     lc = l[1];
   }
   const int r0 = __shfl_sync(IC3_FULL_MASK, lr, i), c0 = __shfl_sync(IC3_FULL_MASK, lc, i);
-  float acc[CPT];
+  float acc[CPT], acc2[CPT];
 #pragma unroll
-  for (int c = 0; c < CPT; ++c) acc[c] = __ldg(bias + lane * CPT + c);
+  for (int c = 0; c < CPT; ++c) {
+    acc[c] = __ldg(bias + lane * CPT + c);
+    acc2[c] = 0.f;
+  }
   for (int w = 0; w < W * W; ++w) {
     const int dy = w / W, dx = w - dy * W;
     const int rr = r0 - v + dy, cc = c0 - v + dx;
@@ -390,19 +419,25 @@ __global__ void __launch_bounds__(256) pp_encoder_index_kernel(ic3_pp_cfg env, i
       const int npred = __popc(here & ((1u << N) - 1u));
       const int nprey = (here >> N) & 1u;
       axpy_row<CPT>(acc, 1.f, wcell + (size_t)(rr * D + cc) * H, lane);
-      if (nprey) axpy_row<CPT>(acc, (float)nprey, wcell + (size_t)(V - 2) * H, lane);
-      if (npred) axpy_row<CPT>(acc, (float)npred, wcell + (size_t)(V - 1) * H, lane);
+      if (split) {          // counts go to the second sum (ic3_policy_cfg.obs_vocab > 0)
+        if (nprey) axpy_row<CPT>(acc2, (float)nprey, wcell + (size_t)(V - 2) * H, lane);
+        if (npred) axpy_row<CPT>(acc2, (float)npred, wcell + (size_t)(V - 1) * H, lane);
+      } else {
+        if (nprey) axpy_row<CPT>(acc, (float)nprey, wcell + (size_t)(V - 2) * H, lane);
+        if (npred) axpy_row<CPT>(acc, (float)npred, wcell + (size_t)(V - 1) * H, lane);
+      }
     } else {
       axpy_row<CPT>(acc, 1.f, wcell + (size_t)(V - 3) * H, lane);
     }
   }
-  store_x<CPT>(acc, x + (size_t)row * H, lane);
+  store_x2<CPT>(acc, acc2, x + (size_t)row * H, lane);
 }
 
 template <int H>
 __global__ void __launch_bounds__(256) tj_encoder_index_kernel(ic3_tj_cfg env, ic3_tj_state st,
                                                                const float* __restrict__ wT,
-                                                               const float* __restrict__ bias, float* __restrict__ x) {
+                                                               const float* __restrict__ bias, float* __restrict__ x,
+                                                               bool split) {
   constexpr int CPT = H / 32;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int row = blockIdx.x * (blockDim.x >> 5) + warp;
@@ -415,14 +450,23 @@ __global__ void __launch_bounds__(256) tj_encoder_index_kernel(ic3_tj_cfg env, i
     lc = st.loc[((size_t)e * N + lane) * 2 + 1];
   }
   const int r0 = __shfl_sync(IC3_FULL_MASK, lr, i), c0 = __shfl_sync(IC3_FULL_MASK, lc, i);
-  float acc[CPT];
+  float acc[CPT], acc2s[CPT];
 #pragma unroll
-  for (int c = 0; c < CPT; ++c) acc[c] = __ldg(bias + lane * CPT + c);
+  for (int c = 0; c < CPT; ++c) {
+    acc[c] = __ldg(bias + lane * CPT + c);
+    acc2s[c] = 0.f;
+  }
+  // split (ic3_policy_cfg.obs_vocab > 0): scalars and car counts form the second sum
   if (st.alive[(size_t)e * N + i]) {
     const float la = (float)st.last_act[(size_t)e * N + i];
     const float ri = (float)st.route_id[(size_t)e * N + i] / (float)(env.npath - 1);
-    if (la != 0.f) axpy_row<CPT>(acc, la, wT, lane);
-    if (ri != 0.f) axpy_row<CPT>(acc, ri, wT + H, lane);
+    if (split) {
+      if (la != 0.f) axpy_row<CPT>(acc2s, la, wT, lane);
+      if (ri != 0.f) axpy_row<CPT>(acc2s, ri, wT + H, lane);
+    } else {
+      if (la != 0.f) axpy_row<CPT>(acc, la, wT, lane);
+      if (ri != 0.f) axpy_row<CPT>(acc, ri, wT + H, lane);
+    }
     for (int w = 0; w < W * W; ++w) {
       const int dy = w / W, dx = w - dy * W;
       const int rr = r0 - v + dy, cc = c0 - v + dx;
@@ -435,10 +479,48 @@ __global__ void __launch_bounds__(256) tj_encoder_index_kernel(ic3_tj_cfg env, i
       }
       // dense order: class index ascending; cls < car_cls always (BASE+2)
       axpy_row<CPT>(acc, 1.f, wcell + (size_t)cls * H, lane);
-      if (cnt) axpy_row<CPT>(acc, (float)cnt, wcell + (size_t)env.car_cls * H, lane);
+      if (cnt) {
+        if (split) axpy_row<CPT>(acc2s, (float)cnt, wcell + (size_t)env.car_cls * H, lane);
+        else axpy_row<CPT>(acc, (float)cnt, wcell + (size_t)env.car_cls * H, lane);
+      }
     }
   }
-  store_x<CPT>(acc, x + (size_t)row * H, lane);
+  store_x2<CPT>(acc, acc2s, x + (size_t)row * H, lane);      // acc2s == 0 when not split: x = acc
+}
+
+// ---------------------------------------------------------------------------
+// class part of the encoder sum per agent position (see ic3_policy_cfg.obs_vocab): thread = hidden unit,
+// same sequence of fp32 additions as the kernels above -> the fused encoder that starts from this table is
+// bit-identical to them.
+// ---------------------------------------------------------------------------
+__global__ void pp_encoder_table_kernel(int D, int v, int H, const float* __restrict__ wT, const float* __restrict__ bias,
+                                        float* __restrict__ table) {
+  const int pos = blockIdx.x, n = threadIdx.x;
+  const int r0 = pos / D, c0 = pos - r0 * D, W = 2 * v + 1, V = D * D + 4;
+  if (n >= H) return;
+  float acc = bias[n];
+  for (int w = 0; w < W * W; ++w) {
+    const int dy = w / W, dx = w - dy * W;
+    const int rr = r0 - v + dy, cc = c0 - v + dx;
+    const int cls = (rr >= 0 && rr < D && cc >= 0 && cc < D) ? rr * D + cc : V - 3;
+    acc = fmaf(1.f, wT[(size_t)(w * V + cls) * H + n], acc);
+  }
+  table[(size_t)pos * H + n] = acc;
+}
+
+__global__ void tj_encoder_table_kernel(ic3_tj_cfg env, int H, const float* __restrict__ wT, const float* __restrict__ bias,
+                                        float* __restrict__ table) {
+  const int pos = blockIdx.x, n = threadIdx.x;
+  const int r0 = pos / env.w, c0 = pos - r0 * env.w, v = env.vision, W = 2 * v + 1, V = env.vocab;
+  if (n >= H) return;
+  float acc = bias[n];
+  for (int w = 0; w < W * W; ++w) {
+    const int dy = w / W, dx = w - dy * W;
+    const int rr = r0 - v + dy, cc = c0 - v + dx;
+    const int cls = (rr >= 0 && rr < env.h && cc >= 0 && cc < env.w) ? env.grid[rr * env.w + cc] : env.outside_cls;
+    acc = fmaf(1.f, wT[(size_t)(2 + w * V + cls) * H + n], acc);
+  }
+  table[(size_t)pos * H + n] = acc;
 }
 
 // ---------------------------------------------------------------------------
@@ -483,6 +565,9 @@ __global__ void pack_kernel(ic3_policy_cfg cfg, ic3_policy_params p, ic3_policy_
 int policy_check(const ic3_policy_cfg* cfg) {
   if (!cfg) return IC3_E_NULL;
   if (cfg->B <= 0 || cfg->N <= 0 || cfg->N > IC3_MAX_AGENTS || cfg->O <= 0) return IC3_E_RANGE;
+  if (cfg->obs_vocab < 0 || cfg->obs_off < 0 || cfg->obs_ncount < 0 ||
+      (cfg->obs_vocab > 0 && cfg->obs_ncount >= cfg->obs_vocab))
+    return IC3_E_RANGE;
   if (cfg->H != 32 && cfg->H != 64 && cfg->H != 128) return IC3_E_UNSUPPORTED;
   if (cfg->nheads < 1 || cfg->nheads > IC3_MAX_HEADS) return IC3_E_RANGE;
   int tot = 1;
@@ -522,8 +607,9 @@ int launch_encoder_dense(const ic3_policy_cfg* cfg, const ic3_policy_packed* w, 
   const int rows = cfg->B * cfg->N;
   const bool vec = (cfg->O % 4 == 0) && ((reinterpret_cast<uintptr_t>(obs) & 15) == 0);
   const int grid = (rows + 7) / 8;
-  if (vec) encoder_dense_kernel<H, true><<<grid, 256, 0, s>>>(obs, w->enc_wT, w->enc_b, x, rows, cfg->O);
-  else encoder_dense_kernel<H, false><<<grid, 256, 0, s>>>(obs, w->enc_wT, w->enc_b, x, rows, cfg->O);
+  const ObsLayout lay{cfg->obs_off, cfg->obs_vocab, cfg->obs_ncount};
+  if (vec) encoder_dense_kernel<H, true><<<grid, 256, 0, s>>>(obs, w->enc_wT, w->enc_b, x, rows, cfg->O, lay);
+  else encoder_dense_kernel<H, false><<<grid, 256, 0, s>>>(obs, w->enc_wT, w->enc_b, x, rows, cfg->O, lay);
   IC3_LAUNCH_CHECK();
   return IC3_OK;
 }
@@ -561,6 +647,50 @@ extern "C" int ic3_policy_pack(const ic3_policy_cfg* cfg, const ic3_policy_param
 
 extern "C" uint64_t ic3_policy_workspace_bytes(const ic3_policy_cfg* cfg) { return ic3_tc_workspace_bytes(cfg); }
 
+// the layout hint, when given, must be the environment's own
+int ic3_pp_layout_check(const ic3_pp_cfg* env, const ic3_policy_cfg* cfg) {
+  if (cfg->obs_vocab == 0) return IC3_OK;
+  return (cfg->obs_off == 0 && cfg->obs_vocab == env->dim * env->dim + 4 && cfg->obs_ncount == 2) ? IC3_OK : IC3_E_RANGE;
+}
+int ic3_tj_layout_check(const ic3_tj_cfg* env, const ic3_policy_cfg* cfg) {
+  if (cfg->obs_vocab == 0) return IC3_OK;
+  return (cfg->obs_off == 2 && cfg->obs_vocab == env->vocab && cfg->obs_ncount == 1 && env->car_cls == env->vocab - 1)
+             ? IC3_OK : IC3_E_RANGE;
+}
+
+extern "C" int ic3_pp_encoder_table(const ic3_pp_cfg* env, const ic3_policy_cfg* cfg, const ic3_policy_packed* w,
+                                    float* table, void* stream) {
+  int rc = policy_check(cfg);
+  if (rc) return rc;
+  rc = packed_check(w);
+  if (rc) return rc;
+  if (!env || !table) return IC3_E_NULL;
+  const int W = 2 * env->vision + 1;
+  if (cfg->O != W * W * (env->dim * env->dim + 4) || cfg->obs_vocab == 0) return IC3_E_RANGE;
+  rc = ic3_pp_layout_check(env, cfg);
+  if (rc) return rc;
+  pp_encoder_table_kernel<<<env->dim * env->dim, cfg->H, 0, (cudaStream_t)stream>>>(env->dim, env->vision, cfg->H, w->enc_wT,
+                                                                                   w->enc_b, table);
+  IC3_LAUNCH_CHECK();
+  return IC3_OK;
+}
+
+extern "C" int ic3_tj_encoder_table(const ic3_tj_cfg* env, const ic3_policy_cfg* cfg, const ic3_policy_packed* w,
+                                    float* table, void* stream) {
+  int rc = policy_check(cfg);
+  if (rc) return rc;
+  rc = packed_check(w);
+  if (rc) return rc;
+  if (!env || !env->grid || !table) return IC3_E_NULL;
+  const int W = 2 * env->vision + 1;
+  if (cfg->O != 2 + W * W * env->vocab || cfg->obs_vocab == 0) return IC3_E_RANGE;
+  rc = ic3_tj_layout_check(env, cfg);
+  if (rc) return rc;
+  tj_encoder_table_kernel<<<env->h * env->w, cfg->H, 0, (cudaStream_t)stream>>>(*env, cfg->H, w->enc_wT, w->enc_b, table);
+  IC3_LAUNCH_CHECK();
+  return IC3_OK;
+}
+
 extern "C" int ic3_encoder_dense(const ic3_policy_cfg* cfg, const ic3_policy_packed* w, const float* obs,
                                  float* x, void* stream) {
   int rc = policy_check(cfg);
@@ -581,12 +711,15 @@ extern "C" int ic3_pp_encoder_index(const ic3_pp_cfg* env, const ic3_pp_state* s
   if (env->B != cfg->B || env->N != cfg->N || env->N >= IC3_MAX_AGENTS) return IC3_E_RANGE;
   const int W = 2 * env->vision + 1;
   if (cfg->O != W * W * (env->dim * env->dim + 4)) return IC3_E_RANGE;
+  rc = ic3_pp_layout_check(env, cfg);
+  if (rc) return rc;
+  const bool split = cfg->obs_vocab > 0;
   const int rows = cfg->B * cfg->N, grid = (rows + 7) / 8;
   cudaStream_t s = (cudaStream_t)stream;
   switch (cfg->H) {
-    case 32: pp_encoder_index_kernel<32><<<grid, 256, 0, s>>>(*env, *st, w->enc_wT, w->enc_b, x); break;
-    case 64: pp_encoder_index_kernel<64><<<grid, 256, 0, s>>>(*env, *st, w->enc_wT, w->enc_b, x); break;
-    case 128: pp_encoder_index_kernel<128><<<grid, 256, 0, s>>>(*env, *st, w->enc_wT, w->enc_b, x); break;
+    case 32: pp_encoder_index_kernel<32><<<grid, 256, 0, s>>>(*env, *st, w->enc_wT, w->enc_b, x, split); break;
+    case 64: pp_encoder_index_kernel<64><<<grid, 256, 0, s>>>(*env, *st, w->enc_wT, w->enc_b, x, split); break;
+    case 128: pp_encoder_index_kernel<128><<<grid, 256, 0, s>>>(*env, *st, w->enc_wT, w->enc_b, x, split); break;
     default: return IC3_E_UNSUPPORTED;
   }
   IC3_LAUNCH_CHECK();
@@ -603,12 +736,15 @@ extern "C" int ic3_tj_encoder_index(const ic3_tj_cfg* env, const ic3_tj_state* s
   if (env->B != cfg->B || env->N != cfg->N) return IC3_E_RANGE;
   const int W = 2 * env->vision + 1;
   if (cfg->O != 2 + W * W * env->vocab) return IC3_E_RANGE;
+  rc = ic3_tj_layout_check(env, cfg);
+  if (rc) return rc;
+  const bool split = cfg->obs_vocab > 0;
   const int rows = cfg->B * cfg->N, grid = (rows + 7) / 8;
   cudaStream_t s = (cudaStream_t)stream;
   switch (cfg->H) {
-    case 32: tj_encoder_index_kernel<32><<<grid, 256, 0, s>>>(*env, *st, w->enc_wT, w->enc_b, x); break;
-    case 64: tj_encoder_index_kernel<64><<<grid, 256, 0, s>>>(*env, *st, w->enc_wT, w->enc_b, x); break;
-    case 128: tj_encoder_index_kernel<128><<<grid, 256, 0, s>>>(*env, *st, w->enc_wT, w->enc_b, x); break;
+    case 32: tj_encoder_index_kernel<32><<<grid, 256, 0, s>>>(*env, *st, w->enc_wT, w->enc_b, x, split); break;
+    case 64: tj_encoder_index_kernel<64><<<grid, 256, 0, s>>>(*env, *st, w->enc_wT, w->enc_b, x, split); break;
+    case 128: tj_encoder_index_kernel<128><<<grid, 256, 0, s>>>(*env, *st, w->enc_wT, w->enc_b, x, split); break;
     default: return IC3_E_UNSUPPORTED;
   }
   IC3_LAUNCH_CHECK();

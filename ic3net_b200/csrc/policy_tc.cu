@@ -141,21 +141,34 @@ struct PrepSrc {
   ic3_tj_state tjs;
   const float* wT;     // encoder.weight^T [O, H]
   const float* bias;   // [H]
+  const float* table;  // [positions, H] class part of the sum per agent position (ic3_*_encoder_table) or NULL
+  int split;           // ic3_policy_cfg.obs_vocab > 0: class terms and count / scalar terms are summed separately
 };
 
 __device__ __forceinline__ void fma4(float4& a, float v, const float4 w) {
   a.x = fmaf(v, w.x, a.x); a.y = fmaf(v, w.y, a.y); a.z = fmaf(v, w.z, a.z); a.w = fmaf(v, w.w, a.w);
 }
 
-template <int XSRC>
+// accumulate into `a` when sel, else into `b` (both stay in registers)
+__device__ __forceinline__ void fma4_sel(bool sel, float4& a, float4& b, float v, const float4 w) {
+  if (sel) fma4(a, v, w);
+  else fma4(b, v, w);
+}
+
+// TAB: the class part of x comes from the per-position table (src.table); the fused encoder then needs neither
+// the x tile in shared memory nor the class feature indices, only the sparse count terms of each row.
+template <int XSRC, bool TAB>
 __global__ void __launch_bounds__(256) prep_kernel(ic3_policy_cfg cfg, ic3_policy_io io, __half* __restrict__ img,
                                                    PrepSrc src) {
+  static_assert(!(TAB && XSRC == XSRC_TENSOR), "the table belongs to the fused index encoder");
   __shared__ float s_gate[PREP_ROWS + 64];
   __shared__ float s_den[PREP_ROWS + 64];
   __shared__ __align__(16) float s_T[PREP_MAX_ENV][TC_H];
   // fused index encoder: per (row, window cell) the feature index of the one-hot class and the counts
-  __shared__ int s_feat[XSRC == XSRC_TENSOR ? 1 : PREP_ROWS * PREP_MAX_WW];
+  __shared__ int s_feat[(XSRC == XSRC_TENSOR || TAB) ? 1 : PREP_ROWS * PREP_MAX_WW];
   __shared__ int s_cnt[XSRC == XSRC_TENSOR ? 1 : PREP_ROWS * PREP_MAX_WW];
+  __shared__ unsigned s_mask[TAB ? PREP_ROWS : 1];    // window cells of the row that hold a count
+  __shared__ int s_pos[TAB ? PREP_ROWS : 1];          // table row of the agent (-1: observation is all zero)
   __shared__ float s_la[XSRC == XSRC_TJ ? PREP_ROWS : 1], s_ri[XSRC == XSRC_TJ ? PREP_ROWS : 1];
   __shared__ int s_live[XSRC == XSRC_TJ ? PREP_ROWS : 1];
   extern __shared__ __align__(16) float s_x[];   // [PREP_ROWS][H] encoder output (index sources only)
@@ -163,6 +176,10 @@ __global__ void __launch_bounds__(256) prep_kernel(ic3_policy_cfg cfg, ic3_polic
   const int R = cfg.B * N;
   const int tile = blockIdx.x >> 1, hb = blockIdx.x & 1;
   const int row0 = tile * TC_M + hb * PREP_ROWS;
+  if (TAB) {
+    if (threadIdx.x < PREP_ROWS) s_mask[threadIdx.x] = 0u;
+    __syncthreads();
+  }
   for (int w = threadIdx.x; w < PREP_ROWS + 64; w += blockDim.x) {
     const int row = row0 - 32 + w;
     float g = 0.f, den = 1.f;
@@ -203,9 +220,13 @@ __global__ void __launch_bounds__(256) prep_kernel(ic3_policy_cfg cfg, ic3_polic
         } else {
           feat = w * V + V - 3;                          // OUTSIDE class
         }
+        if (TAB && w == 0) s_pos[rl] = l[2 * i] * D + l[2 * i + 1];
+      } else if (TAB && w == 0) {
+        s_pos[rl] = -1;
       }
-      s_feat[rl * WW + w] = feat;
+      if (!TAB) s_feat[rl * WW + w] = feat;
       s_cnt[rl * WW + w] = cnt;
+      if (TAB && cnt) atomicOr(&s_mask[rl], 1u << w);
     }
   } else if (XSRC == XSRC_TJ) {   // traffic_junction_env.py:321-366
     const int v = src.tj.vision, W = 2 * v + 1, WW = W * W, V = src.tj.vocab;
@@ -235,39 +256,52 @@ __global__ void __launch_bounds__(256) prep_kernel(ic3_policy_cfg cfg, ic3_polic
           for (int j = 0; j < N; ++j) cnt += (l[2 * j] == rr && l[2 * j + 1] == cc);
         }
         feat = 2 + w * V + cls;
+        if (TAB && w == 0) s_pos[rl] = src.tjs.alive[row] ? l[2 * i] * src.tj.w + l[2 * i + 1] : -1;
+        if (TAB && !src.tjs.alive[row]) cnt = 0;         // dead car: all-zero observation
+      } else if (TAB && w == 0) {
+        s_pos[rl] = -1;
       }
-      s_feat[rl * WW + w] = feat;
+      if (!TAB) s_feat[rl * WW + w] = feat;
       s_cnt[rl * WW + w] = cnt;
+      if (TAB && cnt) atomicOr(&s_mask[rl], 1u << w);
     }
   }
   __syncthreads();
-  if (XSRC != XSRC_TENSOR) {
+  if (XSRC != XSRC_TENSOR && !TAB) {
     // comm.py:119 on the one-hot observation, never materialised: warp per row, lane = 4 consecutive hidden
-    // units, every weight-row read is one coalesced 512-byte request; x lands in shared memory
+    // units, every weight-row read is one coalesced 512-byte request; x lands in shared memory.
+    // xv = bias + class terms (or the per-position table entry: the same additions, done once per weight update),
+    // x2 = count / scalar terms when the layout hint asks for separate sums (else they join xv, in feature order).
     const int gw = threadIdx.x >> 5, gl = threadIdx.x & 31;
     const float4* wq = reinterpret_cast<const float4*>(src.wT) + gl;
+    const bool split = src.split != 0;
     for (int rl = gw; rl < PREP_ROWS; rl += 8) {
       float4 xv = __ldg(reinterpret_cast<const float4*>(src.bias) + gl);
-      if (row0 + rl < R) {
+      float4 x2 = make_float4(0.f, 0.f, 0.f, 0.f);
+      const int row = row0 + rl;
+      if (row < R) {
         if (XSRC == XSRC_PP) {
           const int W = 2 * src.pp.vision + 1, WW = W * W, V = src.pp.dim * src.pp.dim + 4;
+          constexpr bool tab = false;      // (the table path is the TAB specialisation, phase 2 below)
           for (int w = 0; w < WW; ++w) {
             const int feat = s_feat[rl * WW + w], cnt = s_cnt[rl * WW + w];
-            fma4(xv, 1.f, __ldg(wq + (size_t)feat * (TC_H / 4)));
-            if (cnt >> 8) fma4(xv, (float)(cnt >> 8), __ldg(wq + (size_t)(w * V + V - 2) * (TC_H / 4)));     // PREY
-            if (cnt & 255) fma4(xv, (float)(cnt & 255), __ldg(wq + (size_t)(w * V + V - 1) * (TC_H / 4)));  // PREDATOR
+            if (!tab) fma4(xv, 1.f, __ldg(wq + (size_t)feat * (TC_H / 4)));
+            if (cnt >> 8) fma4_sel(split, x2, xv, (float)(cnt >> 8), __ldg(wq + (size_t)(w * V + V - 2) * (TC_H / 4)));     // PREY
+            if (cnt & 255) fma4_sel(split, x2, xv, (float)(cnt & 255), __ldg(wq + (size_t)(w * V + V - 1) * (TC_H / 4)));  // PREDATOR
           }
         } else if (s_live[rl]) {
           const int W = 2 * src.tj.vision + 1, WW = W * W, V = src.tj.vocab;
-          if (s_la[rl] != 0.f) fma4(xv, s_la[rl], __ldg(wq));
-          if (s_ri[rl] != 0.f) fma4(xv, s_ri[rl], __ldg(wq + (TC_H / 4)));
+          constexpr bool tab = false;
+          if (s_la[rl] != 0.f) fma4_sel(split, x2, xv, s_la[rl], __ldg(wq));
+          if (s_ri[rl] != 0.f) fma4_sel(split, x2, xv, s_ri[rl], __ldg(wq + (TC_H / 4)));
           for (int w = 0; w < WW; ++w) {
             const int feat = s_feat[rl * WW + w], cnt = s_cnt[rl * WW + w];
-            fma4(xv, 1.f, __ldg(wq + (size_t)feat * (TC_H / 4)));
-            if (cnt) fma4(xv, (float)cnt, __ldg(wq + (size_t)(2 + w * V + src.tj.car_cls) * (TC_H / 4)));
+            if (!tab) fma4(xv, 1.f, __ldg(wq + (size_t)feat * (TC_H / 4)));
+            if (cnt) fma4_sel(split, x2, xv, (float)cnt, __ldg(wq + (size_t)(2 + w * V + src.tj.car_cls) * (TC_H / 4)));
           }
         }
       }
+      xv.x += x2.x; xv.y += x2.y; xv.z += x2.z; xv.w += x2.w;
       *reinterpret_cast<float4*>(&s_x[rl * TC_H + 4 * gl]) = xv;
     }
   }
@@ -304,8 +338,34 @@ __global__ void __launch_bounds__(256) prep_kernel(ic3_policy_cfg cfg, ic3_polic
     if (row < R) {
       const int e = row / N;
       const bool fr = io.fresh && io.fresh[e];
-      if (XSRC == XSRC_TENSOR) xv = __ldg(reinterpret_cast<const float4*>(io.x + (size_t)row * TC_H) + q);
-      else xv = *reinterpret_cast<const float4*>(&s_x[rl * TC_H + 4 * q]);
+      if (XSRC == XSRC_TENSOR) {
+        xv = __ldg(reinterpret_cast<const float4*>(io.x + (size_t)row * TC_H) + q);
+      } else if (!TAB) {
+        xv = *reinterpret_cast<const float4*>(&s_x[rl * TC_H + 4 * q]);
+      } else {
+        // x = table[position] + (count / scalar terms in feature order): the same additions as the gather above
+        const int pos = s_pos[rl];
+        xv = __ldg(reinterpret_cast<const float4*>(pos >= 0 ? src.table + (size_t)pos * TC_H : src.bias) + q);
+        float4 x2 = zero4;
+        const float4* wq = reinterpret_cast<const float4*>(src.wT) + q;
+        if (XSRC == XSRC_PP) {
+          const int W = 2 * src.pp.vision + 1, WW = W * W, V = src.pp.dim * src.pp.dim + 4;
+          for (unsigned m = s_mask[rl]; m; m &= m - 1) {
+            const int w = __ffs(m) - 1, cnt = s_cnt[rl * WW + w];
+            if (cnt >> 8) fma4(x2, (float)(cnt >> 8), __ldg(wq + (size_t)(w * V + V - 2) * (TC_H / 4)));     // PREY
+            if (cnt & 255) fma4(x2, (float)(cnt & 255), __ldg(wq + (size_t)(w * V + V - 1) * (TC_H / 4)));  // PREDATOR
+          }
+        } else if (pos >= 0) {
+          const int W = 2 * src.tj.vision + 1, WW = W * W, V = src.tj.vocab;
+          if (s_la[rl] != 0.f) fma4(x2, s_la[rl], __ldg(wq));
+          if (s_ri[rl] != 0.f) fma4(x2, s_ri[rl], __ldg(wq + (TC_H / 4)));
+          for (unsigned m = s_mask[rl]; m; m &= m - 1) {
+            const int w = __ffs(m) - 1;
+            fma4(x2, (float)s_cnt[rl * WW + w], __ldg(wq + (size_t)(2 + w * V + src.tj.car_cls) * (TC_H / 4)));
+          }
+        }
+        xv.x += x2.x; xv.y += x2.y; xv.z += x2.z; xv.w += x2.w;
+      }
       if (!fr) hv = __ldg(reinterpret_cast<const float4*>(io.h + (size_t)row * TC_H) + q);
       if (want_s && s_gate[rl + 32] != 0.f) {      // gate 1 => own h is part of T
         const float4 t = *reinterpret_cast<const float4*>(&s_T[e - e_first][4 * q]);
@@ -1252,38 +1312,47 @@ int ic3_tc_policy_step(const ic3_policy_cfg* cfg, const ic3_policy_packed* w, co
   memset(&src, 0, sizeof(src));
   src.wT = w->enc_wT;
   src.bias = w->enc_b;
+  src.split = cfg->obs_vocab > 0;
+  src.table = io->x_table;
+  if (src.table && !src.split) return IC3_E_RANGE;      // the table IS the first of the two sums
   if (io->x) {
-    prep_kernel<XSRC_TENSOR><<<2 * ntiles_pad, 256, 0, s>>>(*cfg, *io, img, src);
+    prep_kernel<XSRC_TENSOR, false><<<2 * ntiles_pad, 256, 0, s>>>(*cfg, *io, img, src);
   } else if (io->pp_env && io->pp_state) {       // fused index encoder, predator-prey
     const int W = 2 * io->pp_env->vision + 1;
     if (W * W > PREP_MAX_WW || io->pp_env->B != cfg->B || io->pp_env->N != cfg->N) return IC3_E_RANGE;
     if (cfg->O != W * W * (io->pp_env->dim * io->pp_env->dim + 4)) return IC3_E_RANGE;
     src.pp = *io->pp_env;
     src.pps = *io->pp_state;
-    {
+    if (int lrc = ic3_pp_layout_check(io->pp_env, cfg)) return lrc;
+    if (src.table) {
+      prep_kernel<XSRC_PP, true><<<2 * ntiles_pad, 256, 0, s>>>(*cfg, *io, img, src);
+    } else {
       static bool cfgd = false;
       if (!cfgd) {
-        cudaError_t e = cudaFuncSetAttribute(prep_kernel<XSRC_PP>, cudaFuncAttributeMaxDynamicSharedMemorySize, PREP_X_BYTES);
+        cudaError_t e = cudaFuncSetAttribute(prep_kernel<XSRC_PP, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, PREP_X_BYTES);
         if (e != cudaSuccess) return (int)e;
         cfgd = true;
       }
+      prep_kernel<XSRC_PP, false><<<2 * ntiles_pad, 256, PREP_X_BYTES, s>>>(*cfg, *io, img, src);
     }
-    prep_kernel<XSRC_PP><<<2 * ntiles_pad, 256, PREP_X_BYTES, s>>>(*cfg, *io, img, src);
   } else if (io->tj_env && io->tj_state) {       // fused index encoder, traffic junction
     const int W = 2 * io->tj_env->vision + 1;
     if (W * W > PREP_MAX_WW || io->tj_env->B != cfg->B || io->tj_env->N != cfg->N) return IC3_E_RANGE;
     if (cfg->O != 2 + W * W * io->tj_env->vocab) return IC3_E_RANGE;
     src.tj = *io->tj_env;
     src.tjs = *io->tj_state;
-    {
+    if (int lrc = ic3_tj_layout_check(io->tj_env, cfg)) return lrc;
+    if (src.table) {
+      prep_kernel<XSRC_TJ, true><<<2 * ntiles_pad, 256, 0, s>>>(*cfg, *io, img, src);
+    } else {
       static bool cfgd = false;
       if (!cfgd) {
-        cudaError_t e = cudaFuncSetAttribute(prep_kernel<XSRC_TJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, PREP_X_BYTES);
+        cudaError_t e = cudaFuncSetAttribute(prep_kernel<XSRC_TJ, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, PREP_X_BYTES);
         if (e != cudaSuccess) return (int)e;
         cfgd = true;
       }
+      prep_kernel<XSRC_TJ, false><<<2 * ntiles_pad, 256, PREP_X_BYTES, s>>>(*cfg, *io, img, src);
     }
-    prep_kernel<XSRC_TJ><<<2 * ntiles_pad, 256, PREP_X_BYTES, s>>>(*cfg, *io, img, src);
   } else {
     return IC3_E_NULL;
   }

@@ -82,6 +82,9 @@ class PredatorPreyEnv(object):
                                   episode=self.episode.data_ptr(), tick=self.tick.data_ptr())
         self.obs_shape = (B, N, W, W, self.vocab_size)
         self.obs_dim = W * W * self.vocab_size
+        # encoder layout hint (ic3_policy_cfg.obs_off / obs_vocab / obs_ncount): cells of V entries, last two = counts
+        self.obs_layout = (0, self.vocab_size, 2)
+        self.obs_positions = self.dim * self.dim
         self.stat = dict()
         return
 

@@ -95,6 +95,9 @@ class TrafficJunctionEnv(object):
                                   completed=self.is_completed.data_ptr(), cars_in_sys=self.cars_in_sys.data_ptr(),
                                   has_failed=self.has_failed.data_ptr(), tick=self.tick.data_ptr())
         self.obs_dim = 2 + W * W * self.vocab_size
+        # encoder layout hint: two scalars, then cells of V entries whose last one (CAR) is a count
+        self.obs_layout = (2, self.vocab_size, 1) if self.CAR_CLASS == self.vocab_size - 1 else (0, 0, 0)
+        self.obs_positions = self.dims[0] * self.dims[1]
         self.obs_shape = (B, N, self.obs_dim)
         self.stat = dict()
         return

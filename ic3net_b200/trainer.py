@@ -58,6 +58,26 @@ class Trainer(object):
         self.grad_window = int(getattr(args, 'grad_window', 40))
         self._buf = None
         self._graph = None
+        # encoder layout of this environment (class terms / counts summed separately, comm.py set_obs_layout) and
+        # the per-position table of the class terms for the fused index encoder, rebuilt when the weights change
+        policy_net.set_obs_layout(*getattr(env.env, 'obs_layout', (0, 0, 0)))
+        self.use_xtable = bool(getattr(args, 'encoder_table', True))
+        self._xtable = None
+        self._xtable_key = None
+
+    def _encoder_table(self, cfg, w):
+        """[positions, H] class part of x per agent position for the CURRENT weights (None when not applicable)."""
+        e, net = self.env.env, self.policy_net
+        if not self.use_xtable or cfg.obs_vocab == 0:
+            return None
+        key = net._packed_key
+        if self._xtable is None:
+            self._xtable = torch.empty(e.obs_positions, net.hid_size, device=e.device)
+        if key != self._xtable_key:
+            fn = _lib.load().ic3_tj_encoder_table if self.is_tj else _lib.load().ic3_pp_encoder_table
+            _lib.check(fn(C.byref(e.cfg), C.byref(cfg), C.byref(w), self._xtable.data_ptr(), _lib.stream()))
+            self._xtable_key = key
+        return self._xtable
 
     # ------------------------------------------------------------------ buffers
     def _alloc(self, T):
@@ -94,6 +114,12 @@ class Trainer(object):
         return b
 
     # ------------------------------------------------------------------ rollout
+    def _fused_x(self):
+        """Index-form observations on the tensor-core policy path: the encoder runs inside the policy step."""
+        dense = self.obs_mode == 'dense' or (self.record_for_grad and self.is_tj)
+        W = 2 * self.env.env.vision + 1
+        return (not dense) and self.policy_net.policy_impl == 'tc' and W * W <= 25
+
     def _enqueue(self, T):
         """Enqueue T lock-step iterations on the current stream (no host sync)."""
         b, e, net, args = self._buf, self.env.env, self.policy_net, self.args
@@ -109,12 +135,12 @@ class Trainer(object):
         rec = self.record_for_grad
         dense = self.obs_mode == 'dense' or (rec and self.is_tj)
         # tensor-core path: the index encoder is fused into the policy step (x never leaves the operand image)
-        W = 2 * e.vision + 1
-        fused_x = (not dense) and ws is not None and W * W <= 25
+        fused_x = self._fused_x()
         src = {}
         if fused_x:
             src = dict(tj_env=C.addressof(e.cfg), tj_state=C.addressof(e.state)) if self.is_tj else \
                 dict(pp_env=C.addressof(e.cfg), pp_state=C.addressof(e.state))
+            src['x_table'] = _lib.ptr(self._encoder_table(cfg, w))
         for t in range(T):
             if rec:
                 b['s_fresh'][t].copy_(b['fresh'])
@@ -184,7 +210,9 @@ class Trainer(object):
         b = self._buf
         self._episode_boundary(epoch)             # trainer.py:28-32, 45-51
         b['err'].zero_()
-        self.policy_net.packed()                  # (re)pack weights outside any graph capture
+        w = self.policy_net.packed()              # (re)pack weights outside any graph capture
+        if self._fused_x():
+            self._encoder_table(self.policy_net.policy_cfg(e.nenvs), w)  # ... and the encoder table with them
         if self.use_graph:
             if self._graph is None:
                 self._enqueue(T)                  # warm-up (lazy function attributes, allocator)

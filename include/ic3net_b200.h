@@ -182,6 +182,15 @@ typedef struct {
   int32_t comm_mask_zero;  /* args.comm_mask_zero (comm.py:39-43) */
   uint32_t env_id0;
   uint64_t seed;
+  /* Observation layout hint for the encoder sum x = b + sum_f obs[f] * W_e[:, f] (comm.py:119).  With
+   * obs_vocab = V > 0 the features f >= obs_off form cells of V entries whose first V - obs_ncount entries
+   * are a one-hot position class and whose last obs_ncount entries are counts: every encoder (dense, index,
+   * fused) then accumulates the class terms and the remaining terms separately,
+   *   x = (b + sum_class ...) + (0 + sum_other ...),  each sum in increasing feature order,
+   * so that the class part can come from a per-position table (ic3_*_encoder_table) and all forms stay
+   * bit-identical.  predator_prey: (0, D*D+4, 2); traffic_junction: (2, vocab, 1).  obs_vocab = 0: one sum. */
+  int32_t obs_off, obs_vocab, obs_ncount;
+  int32_t reserved0;
 } ic3_policy_cfg;
 
 /* Parameters in the reference state_dict layout (device, fp32). */
@@ -234,6 +243,14 @@ int ic3_pp_encoder_index(const ic3_pp_cfg* env, const ic3_pp_state* st, const ic
                          const ic3_policy_packed* w, float* x, void* stream);
 int ic3_tj_encoder_index(const ic3_tj_cfg* env, const ic3_tj_state* st, const ic3_policy_cfg* cfg,
                          const ic3_policy_packed* w, float* x, void* stream);
+/* Class part of the encoder sum per agent position: table[(r*D + c)*H + n] = b[n] + sum over the window cells
+ * (row-major) of W_e[n, cell*V + class(cell)] -- the one-hot grid of predator_prey_env.py:176-186 /
+ * traffic_junction_env.py:300-319 depends on the position alone.  Rebuild after every weight update.
+ * table: [dim*dim, H] (predator_prey) / [h*w, H] (traffic_junction) float32. */
+int ic3_pp_encoder_table(const ic3_pp_cfg* env, const ic3_policy_cfg* cfg, const ic3_policy_packed* w,
+                         float* table, void* stream);
+int ic3_tj_encoder_table(const ic3_tj_cfg* env, const ic3_policy_cfg* cfg, const ic3_policy_packed* w,
+                         float* table, void* stream);
 
 typedef struct {
   const float* x;             /* [B*N, H] encoder output */
@@ -257,6 +274,9 @@ typedef struct {
   const ic3_pp_state* pp_state;
   const ic3_tj_cfg* tj_env;
   const ic3_tj_state* tj_state;
+  /* optional, fused index encoder only: [positions, H] table of ic3_pp_encoder_table / ic3_tj_encoder_table
+   * for the CURRENT weights (device pointer); needs cfg->obs_vocab > 0. */
+  const float* x_table;
 } ic3_policy_io;
 
 /* Scratch the tcgen05 policy path needs for a batch of cfg->B environments (0 when unsupported). */

@@ -141,9 +141,12 @@ def test_select_action_inverse_cdf():
         assert np.array_equal(act[b][ok], want[ok])
 
 
+@pytest.mark.parametrize("hint", [False, True])
 @pytest.mark.parametrize("env_name", ["env_pp_v1", "env_pp_hard", "env_tj_medium_v1", "env_tj_hard"])
-def test_index_encoder_equals_dense_encoder(env_name):
-    """x from the env state (no obs tensor) must be bit-identical to x = encoder(obs)."""
+def test_index_encoder_equals_dense_encoder(env_name, hint):
+    """x from the env state (no obs tensor) must be bit-identical to x = encoder(obs), with and without the
+    observation-layout hint (class terms and counts summed separately); the per-position table of the class
+    terms must be exactly what those kernels add up."""
     import ctypes as C
     from ic3net_b200 import _lib, data
     meta, z = load_golden(env_name)
@@ -154,6 +157,8 @@ def test_index_encoder_equals_dense_encoder(env_name):
     is_tj = args.env_name == "traffic_junction"
     O = w.observation_dim
     net, a, sd = build_net(None, args.nagents, 128, O, (5, 2), True, wseed=8)
+    if hint:
+        net.set_obs_layout(*env.obs_layout)
     obs = w.reset(0)
     env.strict = False
     rs = np.random.RandomState(3)
@@ -175,4 +180,32 @@ def test_index_encoder_equals_dense_encoder(env_name):
         assert torch.equal(xd, xi), (env_name, t)
         ref = cpu(obs).reshape(-1, O).astype(np.float64) @ sd["encoder.weight"].T + sd["encoder.bias"]
         assert close(cpu(xd), ref)
+    if hint:
+        # table[pos] = bias + class terms of an agent standing at pos: check against float64, and against the
+        # dense encoder on an observation that holds only class features (exactly the same additions)
+        tab = torch.empty(env.obs_positions, 128, device="cuda")
+        fn = lib.ic3_tj_encoder_table if is_tj else lib.ic3_pp_encoder_table
+        _lib.check(fn(C.byref(env.cfg), C.byref(cfg), C.byref(pk), tab.data_ptr(), _lib.stream()))
+        off, V, ncount = env.obs_layout
+        o = cpu(obs).reshape(-1, O).copy()
+        cells = o[:, off:].reshape(o.shape[0], -1, V)
+        cells[:, :, V - ncount:] = 0                      # drop the counts ...
+        o[:, :off] = 0                                    # ... and the scalars
+        loc = cpu(env.car_loc if is_tj else env.loc)
+        alive = cpu(env.alive_mask) if is_tj else None
+        rows, want64 = [], []
+        for b_ in range(B):
+            for i in range(args.nagents):
+                if is_tj and not alive[b_, i]:
+                    continue                              # dead cars have an all-zero observation
+                r_, c_ = loc[b_, i]
+                rows.append(b_ * args.nagents + i)
+                want64.append(int(r_) * (env.dims[1] if is_tj else env.dim) + int(c_))
+        if rows:
+            od = torch.from_numpy(o).float().cuda().reshape(B, args.nagents, O).contiguous()
+            xc = torch.empty(B * args.nagents, 128, device="cuda")
+            _lib.check(lib.ic3_encoder_dense(C.byref(cfg), C.byref(pk), od.data_ptr(), xc.data_ptr(), _lib.stream()))
+            assert torch.equal(xc[rows], tab[want64])
+            ref = o[rows].astype(np.float64) @ sd["encoder.weight"].T + sd["encoder.bias"]
+            assert close(cpu(tab[want64]), ref)
     env.err.zero_()

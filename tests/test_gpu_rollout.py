@@ -141,16 +141,23 @@ def test_graph_replay_equals_eager():
     assert np.array_equal(cpu(b3.value), g[2])
 
 
-def test_dense_and_index_rollouts_are_identical():
-    meta, z = load_golden("ep_pp_hard_ic3net")
+@pytest.mark.parametrize("name", ["ep_pp_hard_ic3net", "ep_tj_medium_ic3net", "ep_tj_medium_v1_commnet"])
+def test_dense_and_index_rollouts_are_identical(name):
+    """Dense obs + dense encoder, fused index encoder from the per-position table, fused index encoder without
+    the table: bit-identical rollouts (same additions in the same order, include/ic3net_b200.h obs_vocab)."""
+    meta, z = load_golden(name)
+    if meta["args"]["hid_size"] != 128:
+        pytest.skip("fused encoder is part of the tensor-core path (hid_size 128)")
     res = []
-    for mode in ("index", "dense"):
-        args, env, net, tr, p = build(meta, 24, mode, seed=77)
+    for mode, table in (("index", True), ("index", False), ("dense", True)):
+        args, env, net, tr, p = build(meta, 24, mode, seed=77, encoder_table=table)
         b = tr.rollout(30, 0)
         torch.cuda.synchronize()
+        assert (tr._xtable is not None) == (mode == "index" and table)
         res.append((cpu(b.action).copy(), cpu(b.value).copy(), cpu(b.reward).copy()))
-    assert np.array_equal(res[0][0], res[1][0]) and np.array_equal(res[0][1], res[1][1])
-    assert np.array_equal(res[0][2], res[1][2])
+    for k in (1, 2):
+        assert np.array_equal(res[0][0], res[k][0]) and np.array_equal(res[0][1], res[k][1])
+        assert np.array_equal(res[0][2], res[k][2])
 
 
 def test_pp_hard_full_size_rollout_properties():
