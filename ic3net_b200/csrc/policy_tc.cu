@@ -176,10 +176,12 @@ __global__ void __launch_bounds__(256) prep_kernel(ic3_policy_cfg cfg, ic3_polic
   const int R = cfg.B * N;
   const int tile = blockIdx.x >> 1, hb = blockIdx.x & 1;
   const int row0 = tile * TC_M + hb * PREP_ROWS;
+  ic3_pdl_trigger();
   if (TAB) {
     if (threadIdx.x < PREP_ROWS) s_mask[threadIdx.x] = 0u;
     __syncthreads();
   }
+  ic3_pdl_wait();      // h, masks, env state: written by the previous kernels of the step
   for (int w = threadIdx.x; w < PREP_ROWS + 64; w += blockDim.x) {
     const int row = row0 - 32 + w;
     float g = 0.f, den = 1.f;
@@ -740,13 +742,7 @@ __global__ void __launch_bounds__(TC_P_THREADS, 1) lstm_tc_kernel(ic3_policy_cfg
   // of its 32 hidden units into per-slot partial logits (partial != nullptr  <=>  nout <= 8)
   float* s_hw = reinterpret_cast<float*>(smem + NSTAGE_P * STAGE_BYTES + 256);
   float* s_bias = s_hw + TC_H * HEAD_PAD;
-  load_scaled_bias(s_bias, bias_cat);
-  if (partial) {
-    for (int idx = threadIdx.x; idx < TC_H * HEAD_PAD; idx += blockDim.x) {
-      const int u = idx / HEAD_PAD, o = idx - u * HEAD_PAD;
-      s_hw[idx] = o < nout ? __ldg(head_w + (size_t)o * TC_H + u) : 0.f;
-    }
-  }
+  ic3_pdl_trigger();
   const uint32_t bar_full = smem_u32(bars), bar_empty = smem_u32(bars + NSTAGE_P);
   const uint32_t bar_tfull = smem_u32(bars + 2 * NSTAGE_P), bar_tempty = smem_u32(bars + 2 * NSTAGE_P + 2);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -769,6 +765,16 @@ __global__ void __launch_bounds__(TC_P_THREADS, 1) lstm_tc_kernel(ic3_policy_cfg
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  // barriers and TMEM are set up while the previous kernel (prep) drains; weights (they may have been re-packed by
+  // an earlier kernel of the stream) and the operand image are only touched from here on
+  ic3_pdl_wait();
+  load_scaled_bias(s_bias, bias_cat);
+  if (partial) {
+    for (int idx = threadIdx.x; idx < TC_H * HEAD_PAD; idx += blockDim.x) {
+      const int u = idx / HEAD_PAD, o = idx - u * HEAD_PAD;
+      s_hw[idx] = o < nout ? __ldg(head_w + (size_t)o * TC_H + u) : 0.f;
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -973,13 +979,7 @@ __global__ void __launch_bounds__(TC_P_THREADS, 1) lstm_tc_pair_kernel(ic3_polic
   // of its 32 hidden units into per-slot partial logits (partial != nullptr  <=>  nout <= 8)
   float* s_hw = reinterpret_cast<float*>(smem + PAIR_NSTAGE * PAIR_STAGE_BYTES + 256);
   float* s_bias = s_hw + TC_H * HEAD_PAD;
-  load_scaled_bias(s_bias, bias_cat);
-  if (partial) {
-    for (int idx = threadIdx.x; idx < TC_H * HEAD_PAD; idx += blockDim.x) {
-      const int u = idx / HEAD_PAD, o = idx - u * HEAD_PAD;
-      s_hw[idx] = o < nout ? __ldg(head_w + (size_t)o * TC_H + u) : 0.f;
-    }
-  }
+  ic3_pdl_trigger();
   const uint32_t bar_full = smem_u32(bars), bar_empty = smem_u32(bars + PAIR_NSTAGE);
   const uint32_t bar_pfull = smem_u32(bars + 2 * PAIR_NSTAGE);      // leader: "the peer's stage has landed"
   const uint32_t bar_tfull = smem_u32(bars + 3 * PAIR_NSTAGE), bar_tempty = smem_u32(bars + 3 * PAIR_NSTAGE + 2);
@@ -1005,6 +1005,14 @@ __global__ void __launch_bounds__(TC_P_THREADS, 1) lstm_tc_pair_kernel(ic3_polic
     asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  ic3_pdl_wait();
+  load_scaled_bias(s_bias, bias_cat);
+  if (partial) {
+    for (int idx = threadIdx.x; idx < TC_H * HEAD_PAD; idx += blockDim.x) {
+      const int u = idx / HEAD_PAD, o = idx - u * HEAD_PAD;
+      s_hw[idx] = o < nout ? __ldg(head_w + (size_t)o * TC_H + u) : 0.f;
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -1119,6 +1127,8 @@ __global__ void __launch_bounds__(TC_P_THREADS, 1) lstm_tc_pair_kernel(ic3_polic
 // value, log-softmax per head, inverse-CDF sampling.  One thread per agent row.
 __global__ void __launch_bounds__(128) heads_finish_kernel(ic3_policy_cfg cfg, ic3_policy_packed w, ic3_policy_io io,
                                                             const float* __restrict__ partial) {
+  ic3_pdl_trigger();
+  ic3_pdl_wait();      // the partial logits come from the LSTM kernel
   const long row = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (row >= (long)cfg.B * cfg.N) return;
   float logit[HEAD_PAD];
@@ -1210,7 +1220,7 @@ static int launch_lstm_pair(const ic3_policy_cfg* cfg, const ic3_policy_io* io, 
   static int max_clusters = 0;
   const size_t smem = PAIR_NSTAGE * PAIR_STAGE_BYTES + 256 + TC_H * HEAD_PAD * sizeof(float) + 4 * TC_H * sizeof(float);
   auto kern = lstm_tc_pair_kernel;
-  cudaLaunchAttribute la[1];
+  cudaLaunchAttribute la[2];
   la[0].id = cudaLaunchAttributeClusterDimension;
   la[0].val.clusterDim.x = 2; la[0].val.clusterDim.y = 1; la[0].val.clusterDim.z = 1;
   if (max_clusters == 0) {
@@ -1231,7 +1241,9 @@ static int launch_lstm_pair(const ic3_policy_cfg* cfg, const ic3_policy_io* io, 
   lc.blockDim = dim3(TC_P_THREADS);
   lc.dynamicSmemBytes = smem;
   lc.stream = s;
-  lc.attrs = la; lc.numAttrs = 1;
+  la[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  la[1].val.programmaticStreamSerializationAllowed = 1;
+  lc.attrs = la; lc.numAttrs = ic3_pdl_enabled() ? 2 : 1;
   const __half* b_img = reinterpret_cast<const __half*>(w->lstm_img) + B_IMG_HALFS;   // the pair-layout copy
   cudaError_t e = cudaLaunchKernelEx(&lc, kern, *cfg, *io, a_img, b_img, (const float*)w->bias_cat, nitems,
                                      (const float*)w->head_w, nout, partial);
@@ -1244,7 +1256,7 @@ static int launch_lstm(const ic3_policy_cfg* cfg, const ic3_policy_io* io, const
                        int ntiles_pad, size_t smem, int nout, float* partial, cudaStream_t s) {
   static int max_clusters = 0;
   auto kern = lstm_tc_kernel<CL>;
-  cudaLaunchAttribute la[1];
+  cudaLaunchAttribute la[2];
   la[0].id = cudaLaunchAttributeClusterDimension;
   la[0].val.clusterDim.x = CL; la[0].val.clusterDim.y = 1; la[0].val.clusterDim.z = 1;
   if (max_clusters == 0) {
@@ -1265,7 +1277,9 @@ static int launch_lstm(const ic3_policy_cfg* cfg, const ic3_policy_io* io, const
   lc.blockDim = dim3(TC_P_THREADS);
   lc.dynamicSmemBytes = smem;
   lc.stream = s;
-  lc.attrs = la; lc.numAttrs = 1;
+  la[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  la[1].val.programmaticStreamSerializationAllowed = 1;
+  lc.attrs = la; lc.numAttrs = ic3_pdl_enabled() ? 2 : 1;
   const __half* b_img = reinterpret_cast<const __half*>(w->lstm_img);
   cudaError_t e = cudaLaunchKernelEx(&lc, kern, *cfg, *io, a_img, b_img, (const float*)w->bias_cat, nitems,
                                      (const float*)w->head_w, nout, partial);
@@ -1316,7 +1330,7 @@ int ic3_tc_policy_step(const ic3_policy_cfg* cfg, const ic3_policy_packed* w, co
   src.table = io->x_table;
   if (src.table && !src.split) return IC3_E_RANGE;      // the table IS the first of the two sums
   if (io->x) {
-    prep_kernel<XSRC_TENSOR, false><<<2 * ntiles_pad, 256, 0, s>>>(*cfg, *io, img, src);
+    IC3_LAUNCH_RC(ic3_launch_pdl(prep_kernel<XSRC_TENSOR, false>, dim3(2 * ntiles_pad), dim3(256), 0, s, *cfg, *io, img, src));
   } else if (io->pp_env && io->pp_state) {       // fused index encoder, predator-prey
     const int W = 2 * io->pp_env->vision + 1;
     if (W * W > PREP_MAX_WW || io->pp_env->B != cfg->B || io->pp_env->N != cfg->N) return IC3_E_RANGE;
@@ -1325,7 +1339,7 @@ int ic3_tc_policy_step(const ic3_policy_cfg* cfg, const ic3_policy_packed* w, co
     src.pps = *io->pp_state;
     if (int lrc = ic3_pp_layout_check(io->pp_env, cfg)) return lrc;
     if (src.table) {
-      prep_kernel<XSRC_PP, true><<<2 * ntiles_pad, 256, 0, s>>>(*cfg, *io, img, src);
+      IC3_LAUNCH_RC(ic3_launch_pdl(prep_kernel<XSRC_PP, true>, dim3(2 * ntiles_pad), dim3(256), 0, s, *cfg, *io, img, src));
     } else {
       static bool cfgd = false;
       if (!cfgd) {
@@ -1333,7 +1347,7 @@ int ic3_tc_policy_step(const ic3_policy_cfg* cfg, const ic3_policy_packed* w, co
         if (e != cudaSuccess) return (int)e;
         cfgd = true;
       }
-      prep_kernel<XSRC_PP, false><<<2 * ntiles_pad, 256, PREP_X_BYTES, s>>>(*cfg, *io, img, src);
+      IC3_LAUNCH_RC(ic3_launch_pdl(prep_kernel<XSRC_PP, false>, dim3(2 * ntiles_pad), dim3(256), PREP_X_BYTES, s, *cfg, *io, img, src));
     }
   } else if (io->tj_env && io->tj_state) {       // fused index encoder, traffic junction
     const int W = 2 * io->tj_env->vision + 1;
@@ -1343,7 +1357,7 @@ int ic3_tc_policy_step(const ic3_policy_cfg* cfg, const ic3_policy_packed* w, co
     src.tjs = *io->tj_state;
     if (int lrc = ic3_tj_layout_check(io->tj_env, cfg)) return lrc;
     if (src.table) {
-      prep_kernel<XSRC_TJ, true><<<2 * ntiles_pad, 256, 0, s>>>(*cfg, *io, img, src);
+      IC3_LAUNCH_RC(ic3_launch_pdl(prep_kernel<XSRC_TJ, true>, dim3(2 * ntiles_pad), dim3(256), 0, s, *cfg, *io, img, src));
     } else {
       static bool cfgd = false;
       if (!cfgd) {
@@ -1351,12 +1365,11 @@ int ic3_tc_policy_step(const ic3_policy_cfg* cfg, const ic3_policy_packed* w, co
         if (e != cudaSuccess) return (int)e;
         cfgd = true;
       }
-      prep_kernel<XSRC_TJ, false><<<2 * ntiles_pad, 256, PREP_X_BYTES, s>>>(*cfg, *io, img, src);
+      IC3_LAUNCH_RC(ic3_launch_pdl(prep_kernel<XSRC_TJ, false>, dim3(2 * ntiles_pad), dim3(256), PREP_X_BYTES, s, *cfg, *io, img, src));
     }
   } else {
     return IC3_E_NULL;
   }
-  IC3_LAUNCH_CHECK();
   const size_t smem = NSTAGE_P * STAGE_BYTES + 256 + TC_H * HEAD_PAD * sizeof(float) + 4 * TC_H * sizeof(float);
   int nout = 1;
   for (int k = 0; k < cfg->nheads; ++k) nout += cfg->head_dim[k];
@@ -1374,8 +1387,8 @@ int ic3_tc_policy_step(const ic3_policy_cfg* cfg, const ic3_policy_packed* w, co
   }
   if (rc) return rc;
   if (fused_heads) {
-    heads_finish_kernel<<<(int)((R + 127) / 128), 128, 0, s>>>(*cfg, *w, *io, partial);
-    IC3_LAUNCH_CHECK();
+    IC3_LAUNCH_RC(ic3_launch_pdl(heads_finish_kernel, dim3((unsigned)((R + 127) / 128)), dim3(128), 0, s, *cfg, *w, *io,
+                                 (const float*)partial));
     return IC3_OK;
   }
   const int P = nout <= 8 ? 8 : (nout <= 16 ? 16 : 32);

@@ -116,6 +116,8 @@ template <bool VEC4>
 __global__ void pp_step_kernel(PPArgs a, const int32_t* __restrict__ act, int act_stride,
                                float* __restrict__ reward, float* __restrict__ obs, int32_t* err,
                                RolloutOpt r, int do_step) {
+  ic3_pdl_trigger();
+  ic3_pdl_wait();      // everything below reads state / actions written by the previous kernel of the step
   extern __shared__ uint32_t s_cell[];
   __shared__ int s_r[IC3_MAX_AGENTS + 1], s_c[IC3_MAX_AGENTS + 1];
   const int e = blockIdx.x;
@@ -216,10 +218,11 @@ int pp_launch(const ic3_pp_cfg* cfg, const ic3_pp_state* st, const int32_t* act,
   const bool vec4 = (V % 4 == 0) && ((reinterpret_cast<uintptr_t>(obs) & 15) == 0);
   RolloutOpt ro = make_rollout_opt(r);
   if (vec4)
-    pp_step_kernel<true><<<cfg->B, threads, smem, s>>>(a, act, act_stride, reward, obs, err, ro, do_step);
+    IC3_LAUNCH_RC(ic3_launch_pdl(pp_step_kernel<true>, dim3(cfg->B), dim3(threads), smem, s, a, act, act_stride, reward, obs,
+                                 err, ro, do_step));
   else
-    pp_step_kernel<false><<<cfg->B, threads, smem, s>>>(a, act, act_stride, reward, obs, err, ro, do_step);
-  IC3_LAUNCH_CHECK();
+    IC3_LAUNCH_RC(ic3_launch_pdl(pp_step_kernel<false>, dim3(cfg->B), dim3(threads), smem, s, a, act, act_stride, reward, obs,
+                                 err, ro, do_step));
   return IC3_OK;
 }
 

@@ -90,6 +90,8 @@ __device__ __forceinline__ void tj_write_obs(const ic3_tj_cfg& cfg, const int* s
 __global__ void tj_step_kernel(TJArgs a, const int32_t* __restrict__ act, int act_stride,
                                const uint32_t* __restrict__ draws, float* __restrict__ reward,
                                float* __restrict__ obs, int32_t* err, RolloutOpt r, int do_step) {
+  ic3_pdl_trigger();
+  ic3_pdl_wait();      // everything below reads state / actions written by the previous kernel of the step
   extern __shared__ uint32_t s_cell[];
   __shared__ int s_r[IC3_MAX_AGENTS], s_c[IC3_MAX_AGENTS], s_alive[IC3_MAX_AGENTS], s_rid[IC3_MAX_AGENTS],
       s_lact[IC3_MAX_AGENTS];
@@ -244,8 +246,8 @@ int tj_launch(const ic3_tj_cfg* cfg, const ic3_tj_state* st, const int32_t* act,
   const size_t smem = obs ? (size_t)cfg->N * W * W * sizeof(uint32_t) : 0;
   const int threads = obs ? 128 : 32;
   RolloutOpt ro = make_rollout_opt(r);
-  tj_step_kernel<<<cfg->B, threads, smem, s>>>(a, act, act_stride, draws, reward, obs, err, ro, do_step);
-  IC3_LAUNCH_CHECK();
+  IC3_LAUNCH_RC(ic3_launch_pdl(tj_step_kernel, dim3(cfg->B), dim3(threads), smem, s, a, act, act_stride, draws, reward, obs, err,
+                               ro, do_step));
   return IC3_OK;
 }
 
