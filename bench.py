@@ -210,6 +210,7 @@ def gpu_arm(opts):
     def build(obs_mode, nenvs=None):
         a = make_args(opts.workload, rank, obs_mode, nenvs)
         a.policy_impl = opts.policy_impl
+        a.obs_chunk_mb = opts.obs_chunk_mb
         env = data.init(a.env_name, a)
         a.num_inputs = env.observation_dim
         a.num_actions = [env.num_actions] + ([2] if a.hard_attn else [])
@@ -364,6 +365,7 @@ def gpu_arm(opts):
                                 cuda_graph=bool(opts.graph), policy_impl=net.policy_impl,
                                 l2="per-step working set %.2f GB > 126 MB L2 (inputs larger than L2)"
                                    % ((8 * O + 20 * H) * B * N / 1e9),
+                                obs_chunks=(len(tr._dense_chunks(net.policy_cfg(B))) if opts.obs_mode == "dense" else 0),
                                 weights="random init (torch.manual_seed(0)), reference architecture"),
                     clocks=clk.summary((wall0, wall1)), gpu_launches=launches, e2e=e2e, roofline=roof, kernels=kinfo)
         if alt:
@@ -552,6 +554,9 @@ def main():
                     help="tcgen05 tensor-core policy kernels (default for hid_size 128) or the fp32 SIMT kernel")
     ap.add_argument("--graph", action="store_true", help="replay each episode horizon of the rollout as one CUDA graph")
     ap.add_argument("--quick", action="store_true", help="skip the e2e / index / CPU legs (profiling runs)")
+    ap.add_argument("--obs_chunk_mb", type=float, default=0.0,
+                    help="dense rollout: gather + encode observations in chunks of env slots of at most this size "
+                         "(experiment; 0 = the whole batch at once, the measured optimum)")
     opts = ap.parse_args()
     if opts.impl == "reference":
         return reference_arm(opts)

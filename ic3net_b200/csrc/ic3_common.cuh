@@ -109,5 +109,17 @@ __device__ __forceinline__ uint32_t ic3_word(const uint4& w, int i) {
 // ---------------------------------------------------------------------------
 __device__ __forceinline__ void ic3_st_stream(float4* p, const float4& v) { __stcs(p, v); }
 __device__ __forceinline__ void ic3_st_stream(float* p, float v) { __stcs(p, v); }
+// keep = true: plain write-back store (the consumer kernel follows while the lines are still in L2)
+__device__ __forceinline__ void ic3_st_obs(float4* p, const float4& v, bool keep) {
+  if (keep) *p = v;
+  else __stcs(p, v);
+}
+__device__ __forceinline__ void ic3_st_obs(float* p, float v, bool keep) {
+  if (keep) *p = v;
+  else __stcs(p, v);
+}
+// Observation batches up to this size are written with plain stores so that the encoder launched right after
+// them reads L2 instead of HBM (126 MB L2 on B200); larger ones stream with evict-first stores.
+constexpr size_t IC3_OBS_L2_KEEP_BYTES = (size_t)96 << 20;
 __device__ __forceinline__ float4 ic3_ld_stream(const float4* p) { return __ldcs(p); }
 __device__ __forceinline__ float ic3_ld_stream(const float* p) { return __ldcs(p); }

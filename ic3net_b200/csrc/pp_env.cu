@@ -61,7 +61,7 @@ __global__ void pp_reset_kernel(PPArgs a, const uint8_t* __restrict__ mask) {
 // N*W*W cells, V floats each.  s_cell packs (cls | npred << 16 | nprey << 24).
 template <bool VEC4>
 __device__ __forceinline__ void pp_write_obs(const ic3_pp_cfg& cfg, const int* s_r, const int* s_c,
-                                            uint32_t* s_cell, float* __restrict__ obs_env) {
+                                            uint32_t* s_cell, float* __restrict__ obs_env, bool keep) {
   const int N = cfg.N, D = cfg.dim, v = cfg.vision, W = 2 * v + 1, WW = W * W;
   const int V = D * D + 4, OUTSIDE = D * D + 1;
   const int ncell = N * WW;
@@ -98,14 +98,14 @@ __device__ __forceinline__ void pp_write_obs(const ic3_pp_cfg& cfg, const int* s
         if (q == qp) {  // PREDATOR class = V-1 -> component 3
           o.w = npred;
         }
-        ic3_st_stream(reinterpret_cast<float4*>(dst) + q, o);
+        ic3_st_obs(reinterpret_cast<float4*>(dst) + q, o, keep);
       }
     } else {
       for (int q = lane; q < V; q += 32) {
         float o = (q == cls) ? 1.f : 0.f;
         if (q == V - 2) o = nprey;
         if (q == V - 1) o = npred;
-        ic3_st_stream(dst + q, o);
+        ic3_st_obs(dst + q, o, keep);
       }
     }
   }
@@ -115,7 +115,7 @@ __device__ __forceinline__ void pp_write_obs(const ic3_pp_cfg& cfg, const int* s
 template <bool VEC4>
 __global__ void pp_step_kernel(PPArgs a, const int32_t* __restrict__ act, int act_stride,
                                float* __restrict__ reward, float* __restrict__ obs, int32_t* err,
-                               RolloutOpt r, int do_step) {
+                               RolloutOpt r, int do_step, int keep_l2) {
   ic3_pdl_trigger();
   ic3_pdl_wait();      // everything below reads state / actions written by the previous kernel of the step
   extern __shared__ uint32_t s_cell[];
@@ -193,7 +193,7 @@ __global__ void pp_step_kernel(PPArgs a, const int32_t* __restrict__ act, int ac
   if (obs == nullptr) return;
   __syncthreads();
   const int W = 2 * a.cfg.vision + 1;
-  pp_write_obs<VEC4>(a.cfg, s_r, s_c, s_cell, obs + (size_t)e * N * W * W * (D * D + 4));
+  pp_write_obs<VEC4>(a.cfg, s_r, s_c, s_cell, obs + (size_t)e * N * W * W * (D * D + 4), keep_l2 != 0);
 }
 
 int pp_check(const ic3_pp_cfg* cfg, const ic3_pp_state* st) {
@@ -217,12 +217,14 @@ int pp_launch(const ic3_pp_cfg* cfg, const ic3_pp_state* st, const int32_t* act,
   const int threads = obs ? 256 : 32;
   const bool vec4 = (V % 4 == 0) && ((reinterpret_cast<uintptr_t>(obs) & 15) == 0);
   RolloutOpt ro = make_rollout_opt(r);
+  // small observation batches stay in L2 for the encoder that follows (see IC3_OBS_L2_KEEP_BYTES)
+  const int keep = obs && (size_t)cfg->B * cfg->N * W * W * V * sizeof(float) <= IC3_OBS_L2_KEEP_BYTES;
   if (vec4)
     IC3_LAUNCH_RC(ic3_launch_pdl(pp_step_kernel<true>, dim3(cfg->B), dim3(threads), smem, s, a, act, act_stride, reward, obs,
-                                 err, ro, do_step));
+                                 err, ro, do_step, keep));
   else
     IC3_LAUNCH_RC(ic3_launch_pdl(pp_step_kernel<false>, dim3(cfg->B), dim3(threads), smem, s, a, act, act_stride, reward, obs,
-                                 err, ro, do_step));
+                                 err, ro, do_step, keep));
   return IC3_OK;
 }
 

@@ -49,7 +49,7 @@ __global__ void tj_reset_kernel(TJArgs a, const uint8_t* __restrict__ mask) {
 // s_cell packs (cls | count << 16).
 __device__ __forceinline__ void tj_write_obs(const ic3_tj_cfg& cfg, const int* s_r, const int* s_c,
                                             const int* s_alive, const int* s_rid, const int* s_lact,
-                                            uint32_t* s_cell, float* __restrict__ obs_env) {
+                                            uint32_t* s_cell, float* __restrict__ obs_env, bool keep) {
   const int N = cfg.N, v = cfg.vision, W = 2 * v + 1, WW = W * W, V = cfg.vocab;
   const int O = 2 + WW * V;
   const int ncell = N * WW;
@@ -76,7 +76,7 @@ __device__ __forceinline__ void tj_write_obs(const ic3_tj_cfg& cfg, const int* s
     for (int q = lane; q < V; q += 32) {
       float o = (q == cls) ? 1.f : 0.f;
       if (q == cfg.car_cls) o += cnt;
-      ic3_st_stream(dst + q, live ? o : 0.f);
+      ic3_st_obs(dst + q, live ? o : 0.f, keep);
     }
   }
   for (int i = threadIdx.x; i < N; i += blockDim.x) {
@@ -89,7 +89,7 @@ __device__ __forceinline__ void tj_write_obs(const ic3_tj_cfg& cfg, const int* s
 
 __global__ void tj_step_kernel(TJArgs a, const int32_t* __restrict__ act, int act_stride,
                                const uint32_t* __restrict__ draws, float* __restrict__ reward,
-                               float* __restrict__ obs, int32_t* err, RolloutOpt r, int do_step) {
+                               float* __restrict__ obs, int32_t* err, RolloutOpt r, int do_step, int keep_l2) {
   ic3_pdl_trigger();
   ic3_pdl_wait();      // everything below reads state / actions written by the previous kernel of the step
   extern __shared__ uint32_t s_cell[];
@@ -221,7 +221,7 @@ __global__ void tj_step_kernel(TJArgs a, const int32_t* __restrict__ act, int ac
   if (obs == nullptr) return;
   __syncthreads();
   const int W = 2 * cfg.vision + 1;
-  tj_write_obs(cfg, s_r, s_c, s_alive, s_rid, s_lact, s_cell, obs + (size_t)e * N * (2 + W * W * cfg.vocab));
+  tj_write_obs(cfg, s_r, s_c, s_alive, s_rid, s_lact, s_cell, obs + (size_t)e * N * (2 + W * W * cfg.vocab), keep_l2 != 0);
 }
 
 int tj_check(const ic3_tj_cfg* cfg, const ic3_tj_state* st) {
@@ -246,8 +246,9 @@ int tj_launch(const ic3_tj_cfg* cfg, const ic3_tj_state* st, const int32_t* act,
   const size_t smem = obs ? (size_t)cfg->N * W * W * sizeof(uint32_t) : 0;
   const int threads = obs ? 128 : 32;
   RolloutOpt ro = make_rollout_opt(r);
+  const int keep = obs && (size_t)cfg->B * cfg->N * (2 + W * W * cfg->vocab) * sizeof(float) <= IC3_OBS_L2_KEEP_BYTES;
   IC3_LAUNCH_RC(ic3_launch_pdl(tj_step_kernel, dim3(cfg->B), dim3(threads), smem, s, a, act, act_stride, draws, reward, obs, err,
-                               ro, do_step));
+                               ro, do_step, keep));
   return IC3_OK;
 }
 

@@ -102,6 +102,17 @@ class TrafficJunctionEnv(object):
         self.stat = dict()
         return
 
+
+    def chunk_view(self, k0, k1):
+        """(cfg, state) of the env slots [k0, k1): the same device memory, for kernels run on a slice of the batch."""
+        cfg = _lib.TJCfg.from_buffer_copy(self.cfg)
+        cfg.B, cfg.env_id0 = k1 - k0, self.cfg.env_id0 + k0
+        sl = lambda t: t[k0:k1].data_ptr()
+        st = _lib.TJState(loc=sl(self.car_loc), alive=sl(self.alive_mask), wait=sl(self.wait), route_id=sl(self.route_id),
+                          route_pos=sl(self.car_route_loc), last_act=sl(self.car_last_act),
+                          completed=sl(self.is_completed), cars_in_sys=sl(self.cars_in_sys),
+                          has_failed=sl(self.has_failed), tick=sl(self.tick))
+        return cfg, st
     def _spawn_thr(self):
         # np.random.uniform() <= add_rate (:375) on 24-bit uniforms u = k * 2**-24
         return min(max(int(math.floor(self.add_rate * (2.0 ** 24))), 0), 0xFFFFFFFF) if self.add_rate >= 0 else 0
