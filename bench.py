@@ -351,7 +351,11 @@ def gpu_arm(opts):
             del tr2, net2, env2
 
         # ---- e2e: the public, reference-shaped API with host-side actions / rewards ----
+        # (runs on rank 0 only -- this whole block does; for N > 1 the number is that rank's GPU driven through
+        #  the public API while the other ranks wait, and says so)
         e2e = None if opts.quick else e2e_loop(a, env, net, min(K, 200), np, torch, select_action)
+        if e2e and world > 1:
+            e2e["scope"] = "rank 0 only (one GPU of the %d); ranks are independent replicas of this loop" % world
 
         # ---- CPU baseline (bounded sample of the same workload on the host cores) ----
         cores = host_cores()
