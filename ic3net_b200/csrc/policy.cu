@@ -304,6 +304,21 @@ struct ObsLayout {
     if (f < off) return false;
     return ((f - off) % V) < V - ncount;
   }
+  // four consecutive features f0 .. f0+3 with ONE integer division (V >= 4, checked by policy_check)
+  __device__ __forceinline__ void is_class4(int f0, bool (&c)[4]) const {
+    if (V <= 0) {
+      c[0] = c[1] = c[2] = c[3] = true;
+      return;
+    }
+    const int r = f0 - off;                 // negative only for the scalar features in front of the cells
+    const int m = r >= 0 ? r % V : r;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      int rk = m + k;
+      if (rk >= V) rk -= V;
+      c[k] = rk >= 0 && rk < V - ncount;
+    }
+  }
 };
 
 template <int CPT>
@@ -352,10 +367,12 @@ __global__ void __launch_bounds__(256) encoder_dense_kernel(const float* __restr
           const float sz = __shfl_sync(IC3_FULL_MASK, v[u].z, src), sw = __shfl_sync(IC3_FULL_MASK, v[u].w, src);
           const int f0 = (base + u * 32 + src) * 4;
           const float* wr = wT + (size_t)f0 * H;
-          if (sx != 0.f) { if (lay.is_class(f0)) axpy_row<CPT>(acc, sx, wr, lane); else axpy_row<CPT>(acc2, sx, wr, lane); }
-          if (sy != 0.f) { if (lay.is_class(f0 + 1)) axpy_row<CPT>(acc, sy, wr + H, lane); else axpy_row<CPT>(acc2, sy, wr + H, lane); }
-          if (sz != 0.f) { if (lay.is_class(f0 + 2)) axpy_row<CPT>(acc, sz, wr + 2 * H, lane); else axpy_row<CPT>(acc2, sz, wr + 2 * H, lane); }
-          if (sw != 0.f) { if (lay.is_class(f0 + 3)) axpy_row<CPT>(acc, sw, wr + 3 * H, lane); else axpy_row<CPT>(acc2, sw, wr + 3 * H, lane); }
+          bool cl[4];
+          lay.is_class4(f0, cl);
+          if (sx != 0.f) { if (cl[0]) axpy_row<CPT>(acc, sx, wr, lane); else axpy_row<CPT>(acc2, sx, wr, lane); }
+          if (sy != 0.f) { if (cl[1]) axpy_row<CPT>(acc, sy, wr + H, lane); else axpy_row<CPT>(acc2, sy, wr + H, lane); }
+          if (sz != 0.f) { if (cl[2]) axpy_row<CPT>(acc, sz, wr + 2 * H, lane); else axpy_row<CPT>(acc2, sz, wr + 2 * H, lane); }
+          if (sw != 0.f) { if (cl[3]) axpy_row<CPT>(acc, sw, wr + 3 * H, lane); else axpy_row<CPT>(acc2, sw, wr + 3 * H, lane); }
         }
       }
     }
@@ -568,7 +585,7 @@ int policy_check(const ic3_policy_cfg* cfg) {
   if (!cfg) return IC3_E_NULL;
   if (cfg->B <= 0 || cfg->N <= 0 || cfg->N > IC3_MAX_AGENTS || cfg->O <= 0) return IC3_E_RANGE;
   if (cfg->obs_vocab < 0 || cfg->obs_off < 0 || cfg->obs_ncount < 0 ||
-      (cfg->obs_vocab > 0 && cfg->obs_ncount >= cfg->obs_vocab))
+      (cfg->obs_vocab > 0 && (cfg->obs_ncount >= cfg->obs_vocab || cfg->obs_vocab < 4)))
     return IC3_E_RANGE;
   if (cfg->H != 32 && cfg->H != 64 && cfg->H != 128) return IC3_E_UNSUPPORTED;
   if (cfg->nheads < 1 || cfg->nheads > IC3_MAX_HEADS) return IC3_E_RANGE;
