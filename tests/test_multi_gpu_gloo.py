@@ -119,3 +119,70 @@ def test_stat_packing_roundtrip():
     out = unpack_stat(vec, shapes, {})
     assert out['num_steps'] == 123456789 and out['success'] == 3 and out['add_rate'] == 0.05
     assert np.array_equal(out['reward'], s['reward']) and 'name' not in out
+
+
+class FlatOptCPU(object):
+    """CPU stand-in for ic3net_b200.optim.FlatRMSprop (same surface: flat_grads, zero_grad, step(grad_div)); the
+    update is the torch formula of oracle/optim.py so the world-size-2 result can be compared with `expected`."""
+
+    def __init__(self, params, lr, alpha=0.97, eps=1e-6):
+        self.params = list(params)
+        self.lr, self.alpha, self.eps = lr, alpha, eps
+        self._off, n = [], 0
+        for p in self.params:
+            self._off.append(n)
+            n += p.numel()
+        self.flat_grads = torch.zeros(n)
+        self.flat_sq = torch.zeros(n)
+        self.seen = torch.zeros(n, dtype=torch.bool)
+        for p, off in zip(self.params, self._off):
+            p.grad = self.flat_grads[off:off + p.numel()].view_as(p)
+
+    def zero_grad(self, set_to_none=False):
+        self.flat_grads.zero_()
+
+    def step(self, grad_div=1.0):
+        g = self.flat_grads / grad_div
+        self.flat_sq.mul_(self.alpha).addcmul_(g, g, value=1 - self.alpha)
+        upd = self.lr * g / (self.flat_sq.sqrt() + self.eps)
+        with torch.no_grad():
+            for p, off in zip(self.params, self._off):
+                p.sub_(upd[off:off + p.numel()].view_as(p))
+
+
+class FlatFakeTrainer(FakeTrainer):
+    def __init__(self, rank):
+        super().__init__(rank)
+        self.optimizer = FlatOptCPU(self.net.parameters(), lr=0.01)
+
+
+def _flat_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from ic3net_b200.multi_gpu import MultiGPUTrainer
+    import argparse
+    mt = MultiGPUTrainer(argparse.Namespace(random=False), lambda: FlatFakeTrainer(rank))
+    stat = mt.train_batch(0)
+    q.put((rank, int(stat['num_steps']), [p.detach().numpy().copy() for p in mt.trainer.params], mt.collectives))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_reduction_flat_gradient_buffer():
+    """The FlatRMSprop fast path of MultiGPUTrainer: the flat gradient buffer is all-reduced in place, the division
+    by the GLOBAL step count happens inside optimizer.step(grad_div) -- same result as multi_processing.py:90-97."""
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    ps = [ctx.Process(target=_flat_worker, args=(r, world, port, q)) for r in range(world)]
+    [p.start() for p in ps]
+    res = sorted([q.get(timeout=120) for _ in ps], key=lambda x: x[0])
+    [p.join(timeout=60) for p in ps]
+    stat, params = expected(world)
+    for rank, nsteps, ps_, ncoll in res:
+        assert ncoll == 1 and nsteps == stat['num_steps']
+        for a, b in zip(ps_, params):
+            assert np.allclose(a, b.numpy(), rtol=1e-6, atol=1e-7)
+    for a, b in zip(res[0][2], res[1][2]):
+        assert np.array_equal(a, b)
