@@ -191,3 +191,45 @@ def test_rmsprop_golden():
             assert np.allclose(sq[i], z["v_%d" % i], rtol=1e-12, atol=0)
         else:                                   # never touched: parameter unchanged, no state
             assert np.array_equal(params[i], z["p0_%d" % i])
+
+
+@pytest.mark.parametrize("name", golden_names("grad_"))
+def test_manual_bptt_matches_reference_gradients(name):
+    """oracle/bptt.py (explicit per-step backward formulas = the arithmetic of hand-written BPTT kernels) against
+    the gradients of the reference's own Trainer.compute_grad and against the autograd oracle."""
+    from oracle import bptt
+    from oracle import grad as ograd
+    from oracle.rollout import run_episode
+    meta, z = load_golden(name)
+    args = ns(meta["args"])
+    is_tj = args.env_name == "traffic_junction"
+    sd = make_weights(meta["weights_seed"], meta["obs_dim"], args.hid_size, meta["heads"], args.comm_init)
+    p = policy.params_to_f64(sd)
+    env = make_oracle_env(args, tj_tables(z) if is_tj else None)
+    eps, tick, k = [], 0, 0
+    while tick < meta["num_steps"]:
+        ep = run_episode(env, p, args, meta["seed"], meta["env_id"], epoch=0, tick0=tick, episode=k)
+        eps.append(ep)
+        tick += ep["num_steps"]
+        k += 1
+    g, st = bptt.compute_grad_manual(p, eps, args)
+    assert np.isclose(st["action_loss"], meta["action_loss"], rtol=1e-9, atol=1e-9)
+    assert np.isclose(st["value_loss"], meta["value_loss"], rtol=1e-9, atol=1e-9)
+    assert np.isclose(st["entropy"], meta["entropy"], rtol=1e-9, atol=1e-9)
+    checked = 0
+    for key in z.files:
+        if key.startswith("g_"):
+            assert np.allclose(g[key[2:]], z[key], rtol=1e-8, atol=1e-10), key
+            checked += 1
+        elif key.startswith("gsample_"):
+            q = g[key[8:]]
+            assert np.allclose(q.ravel()[::max(1, q.size // 2048)][:2048], z[key], rtol=1e-8, atol=1e-10), key
+            assert np.allclose([q.sum(), np.abs(q).sum(), (q ** 2).sum()], z["gsum_" + key[8:]], rtol=1e-8)
+            checked += 1
+    assert checked >= 8
+    ga, _, _ = ograd.compute_grad(p, eps, args)
+    for key, v in ga.items():
+        if v is None:
+            assert g[key] is None
+        else:
+            assert np.allclose(g[key], v, rtol=1e-9, atol=1e-11), key
