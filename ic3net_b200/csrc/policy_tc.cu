@@ -272,8 +272,8 @@ __global__ void __launch_bounds__(256) prep_kernel(ic3_policy_cfg cfg, ic3_polic
   if (XSRC != XSRC_TENSOR && !TAB) {
     // comm.py:119 on the one-hot observation, never materialised: warp per row, lane = 4 consecutive hidden
     // units, every weight-row read is one coalesced 512-byte request; x lands in shared memory.
-    // xv = bias + class terms (or the per-position table entry: the same additions, done once per weight update),
-    // x2 = count / scalar terms when the layout hint asks for separate sums (else they join xv, in feature order).
+    // xv = bias + class terms, x2 = count / scalar terms when the layout hint asks for separate sums (else they join
+    // xv, in feature order).  (With the per-position table this whole phase is skipped: TAB specialisation below.)
     const int gw = threadIdx.x >> 5, gl = threadIdx.x & 31;
     const float4* wq = reinterpret_cast<const float4*>(src.wT) + gl;
     const bool split = src.split != 0;
@@ -284,21 +284,19 @@ __global__ void __launch_bounds__(256) prep_kernel(ic3_policy_cfg cfg, ic3_polic
       if (row < R) {
         if (XSRC == XSRC_PP) {
           const int W = 2 * src.pp.vision + 1, WW = W * W, V = src.pp.dim * src.pp.dim + 4;
-          constexpr bool tab = false;      // (the table path is the TAB specialisation, phase 2 below)
           for (int w = 0; w < WW; ++w) {
             const int feat = s_feat[rl * WW + w], cnt = s_cnt[rl * WW + w];
-            if (!tab) fma4(xv, 1.f, __ldg(wq + (size_t)feat * (TC_H / 4)));
+            fma4(xv, 1.f, __ldg(wq + (size_t)feat * (TC_H / 4)));
             if (cnt >> 8) fma4_sel(split, x2, xv, (float)(cnt >> 8), __ldg(wq + (size_t)(w * V + V - 2) * (TC_H / 4)));     // PREY
             if (cnt & 255) fma4_sel(split, x2, xv, (float)(cnt & 255), __ldg(wq + (size_t)(w * V + V - 1) * (TC_H / 4)));  // PREDATOR
           }
         } else if (s_live[rl]) {
           const int W = 2 * src.tj.vision + 1, WW = W * W, V = src.tj.vocab;
-          constexpr bool tab = false;
           if (s_la[rl] != 0.f) fma4_sel(split, x2, xv, s_la[rl], __ldg(wq));
           if (s_ri[rl] != 0.f) fma4_sel(split, x2, xv, s_ri[rl], __ldg(wq + (TC_H / 4)));
           for (int w = 0; w < WW; ++w) {
             const int feat = s_feat[rl * WW + w], cnt = s_cnt[rl * WW + w];
-            if (!tab) fma4(xv, 1.f, __ldg(wq + (size_t)feat * (TC_H / 4)));
+            fma4(xv, 1.f, __ldg(wq + (size_t)feat * (TC_H / 4)));
             if (cnt) fma4_sel(split, x2, xv, (float)cnt, __ldg(wq + (size_t)(2 + w * V + src.tj.car_cls) * (TC_H / 4)));
           }
         }
