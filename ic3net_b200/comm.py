@@ -12,7 +12,6 @@ variants raise.  The rollout forward is inference-only (the reference detaches w
 it samples from, action_utils.py:35); gradients are taken by the trainer.
 """
 import ctypes as C
-import math
 
 import numpy as np
 import torch

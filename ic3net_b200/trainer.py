@@ -26,7 +26,6 @@ import ctypes as C
 import math
 from collections import namedtuple
 
-import numpy as np
 import torch
 import torch.nn.functional as F
 

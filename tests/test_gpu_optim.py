@@ -1,6 +1,5 @@
 """RMSprop step + checkpoint format: the fused flat-buffer kernel against torch.optim.RMSprop
 fixtures, the trainer's update through it, and save / load interchange with the reference's formats."""
-import ctypes as C
 import io
 
 import numpy as np
