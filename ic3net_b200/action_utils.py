@@ -14,22 +14,22 @@ from . import _lib
 
 
 def parse_action_args(args):
-    # action_utils.py:5-25
+    """Derive ``args.continuous`` / ``args.naction_heads`` (action_utils.py:5-25).  A discrete environment
+    (``num_actions[0] > 0``) contributes one head per action dimension; otherwise ``--nactions`` decides: "1" means
+    continuous control, "k" means ``dim_actions`` heads of k actions, "a:b:..." lists the heads explicitly."""
     if args.num_actions[0] > 0:
         args.continuous = False
-        args.naction_heads = [int(args.num_actions[i]) for i in range(args.dim_actions)]
+        args.naction_heads = [int(args.num_actions[d]) for d in range(args.dim_actions)]
+        return
+    spec = [int(tok) for tok in args.nactions.split(':')]        # int('') raises ValueError like the reference
+    if len(spec) > 1:
+        args.continuous, args.naction_heads = False, spec
+    elif spec[0] == 1:
+        args.continuous = True
+    elif spec[0] > 1:
+        args.continuous, args.naction_heads = False, [spec[0]] * args.dim_actions
     else:
-        actions_heads = args.nactions.split(':')
-        if len(actions_heads) == 1 and int(actions_heads[0]) == 1:
-            args.continuous = True
-        elif len(actions_heads) == 1 and int(actions_heads[0]) > 1:
-            args.continuous = False
-            args.naction_heads = [int(actions_heads[0]) for _ in range(args.dim_actions)]
-        elif len(actions_heads) > 1:
-            args.continuous = False
-            args.naction_heads = [int(i) for i in actions_heads]
-        else:
-            raise RuntimeError("--nactions wrong format!")
+        raise RuntimeError("--nactions wrong format!")
 
 
 _ticks = {}

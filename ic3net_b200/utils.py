@@ -10,21 +10,23 @@ LogField = namedtuple('LogField', ('data', 'plot', 'x_axis', 'divide_by'))
 
 
 def merge_stat(src, dest):
-    # utils.py:15-29: numbers and arrays add, everything else is collected in lists
-    for k, v in src.items():
-        if k not in dest:
-            dest[k] = v
-        elif isinstance(v, numbers.Number):
-            dest[k] = dest.get(k, 0) + v
-        elif isinstance(v, np.ndarray):
-            dest[k] = dest.get(k, 0) + v
+    """Fold ``src`` into ``dest`` in place with the reference's rules (utils.py:15-29): a key new to ``dest`` is
+    taken over as is; numbers and numpy arrays accumulate by ``+``; anything else is gathered into a list (two lists
+    are concatenated, a value is appended to an existing list, two plain values become a two-element list)."""
+    for key, val in src.items():
+        if key not in dest:
+            dest[key] = val
+            continue
+        if isinstance(val, (numbers.Number, np.ndarray)):
+            dest[key] = dest[key] + val
+            continue
+        cur = dest[key]
+        if not isinstance(cur, list):
+            dest[key] = [cur, val]
+        elif isinstance(val, list):
+            cur.extend(val)
         else:
-            if isinstance(dest[k], list) and isinstance(v, list):
-                dest[k].extend(v)
-            elif isinstance(dest[k], list):
-                dest[k].append(v)
-            else:
-                dest[k] = [dest[k], v]
+            cur.append(val)
 
 
 def init_args_for_env(parser, argv=None):

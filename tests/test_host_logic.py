@@ -1,0 +1,114 @@
+"""CPU tests of the host-side glue the rollout's callers rely on: merge_stat (utils.py:15-29) and
+parse_action_args (action_utils.py:5-25) -- fixed expectations, plus a differential check against the reference's
+own functions when /root/reference is present (it is in the build container, not on the GPU box)."""
+import argparse
+import copy
+import importlib.util
+import os
+
+import numpy as np
+import pytest
+
+from ic3net_b200.action_utils import parse_action_args
+from ic3net_b200.utils import merge_stat
+
+REF = "/root/reference"
+
+
+def _ref_module(name):
+    path = os.path.join(REF, name + ".py")
+    if not os.path.exists(path):
+        return None
+    spec = importlib.util.spec_from_file_location("_ref_" + name, path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+STAT_CASES = [
+    (dict(a=1, b=2.5), dict()),
+    (dict(a=1, r=np.array([1.0, 2.0])), dict(a=4, r=np.array([0.5, 0.5]))),
+    (dict(s="x"), dict(s="y")),
+    (dict(s="x"), dict(s=["y"])),
+    (dict(s=["x", "z"]), dict(s=["y"])),
+    (dict(s=["x"]), dict(s="y")),
+    (dict(n=3, new=np.zeros(2)), dict(n=np.array([1, 1]))),
+    (dict(flag=True), dict(flag=2)),
+]
+
+
+def _same(a, b):
+    assert a.keys() == b.keys()
+    for k in a:
+        if isinstance(a[k], np.ndarray) or isinstance(b[k], np.ndarray):
+            assert np.array_equal(a[k], b[k]) and type(a[k]) is type(b[k]), k
+        else:
+            assert a[k] == b[k] and type(a[k]) is type(b[k]), k
+
+
+def test_merge_stat_rules():
+    d = dict(a=4, r=np.array([0.5, 0.5]))
+    merge_stat(dict(a=1, r=np.array([1.0, 2.0]), new="v"), d)
+    assert d["a"] == 5 and np.array_equal(d["r"], [1.5, 2.5]) and d["new"] == "v"
+    d = dict(s="y")
+    merge_stat(dict(s="x"), d)
+    assert d["s"] == ["y", "x"]
+    merge_stat(dict(s="z"), d)
+    assert d["s"] == ["y", "x", "z"]
+    merge_stat(dict(s=["p", "q"]), d)
+    assert d["s"] == ["y", "x", "z", "p", "q"]
+    d = dict(s="y")
+    merge_stat(dict(s=["x"]), d)
+    assert d["s"] == ["y", ["x"]]                       # a list merged into a plain value nests (reference quirk)
+
+
+@pytest.mark.parametrize("case", range(len(STAT_CASES)))
+def test_merge_stat_matches_reference(case):
+    ref = _ref_module("utils")
+    if ref is None:
+        pytest.skip("reference checkout not present")
+    src, dest = STAT_CASES[case]
+    d1, d2 = copy.deepcopy(dest), copy.deepcopy(dest)
+    merge_stat(copy.deepcopy(src), d1)
+    ref.merge_stat(copy.deepcopy(src), d2)
+    _same(d1, d2)
+
+
+ACTION_CASES = [
+    dict(num_actions=[5], dim_actions=1, nactions="1"),
+    dict(num_actions=[5, 2], dim_actions=2, nactions="1"),
+    dict(num_actions=[2, 2], dim_actions=1, nactions="1"),
+    dict(num_actions=[0], dim_actions=1, nactions="1"),
+    dict(num_actions=[0], dim_actions=3, nactions="4"),
+    dict(num_actions=[-1], dim_actions=2, nactions="3:5"),
+    dict(num_actions=[0], dim_actions=1, nactions="0"),
+    dict(num_actions=[0], dim_actions=1, nactions=""),
+]
+
+
+def _run(fn, kw):
+    a = argparse.Namespace(**copy.deepcopy(kw))
+    try:
+        fn(a)
+    except Exception as e:                               # noqa: BLE001 - the exception type is part of the behaviour
+        return type(e).__name__, None
+    return None, (getattr(a, "continuous", None), getattr(a, "naction_heads", None))
+
+
+def test_parse_action_args_rules():
+    assert _run(parse_action_args, ACTION_CASES[0]) == (None, (False, [5]))
+    assert _run(parse_action_args, ACTION_CASES[1]) == (None, (False, [5, 2]))
+    assert _run(parse_action_args, ACTION_CASES[2]) == (None, (False, [2]))
+    assert _run(parse_action_args, ACTION_CASES[3]) == (None, (True, None))
+    assert _run(parse_action_args, ACTION_CASES[4]) == (None, (False, [4, 4, 4]))
+    assert _run(parse_action_args, ACTION_CASES[5]) == (None, (False, [3, 5]))
+    assert _run(parse_action_args, ACTION_CASES[6])[0] == "RuntimeError"
+    assert _run(parse_action_args, ACTION_CASES[7])[0] == "ValueError"
+
+
+@pytest.mark.parametrize("case", range(len(ACTION_CASES)))
+def test_parse_action_args_matches_reference(case):
+    ref = _ref_module("action_utils")
+    if ref is None:
+        pytest.skip("reference checkout not present")
+    assert _run(parse_action_args, ACTION_CASES[case]) == _run(ref.parse_action_args, ACTION_CASES[case])
