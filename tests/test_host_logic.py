@@ -112,3 +112,80 @@ def test_parse_action_args_matches_reference(case):
     if ref is None:
         pytest.skip("reference checkout not present")
     assert _run(parse_action_args, ACTION_CASES[case]) == _run(ref.parse_action_args, ACTION_CASES[case])
+
+
+# ---- GymWrapper on duck-typed environments (no GPU needed) ---------------------------------------------
+class _FakeEnv(object):
+    """Minimal batched env: records what the wrapper passes down."""
+
+    def __init__(self, spaces_mod, kind, nenvs=3, nagents=4, takes_epoch=False):
+        sp = spaces_mod
+        self.nenvs, self.n = nenvs, nagents
+        if kind == "pp":                                   # predator_prey_env.py:95,107
+            self.observation_space = sp.Box(low=0, high=1, shape=(29, 3, 3), dtype=int)
+            self.action_space = sp.MultiDiscrete([5])
+        elif kind == "tj":                                 # traffic_junction_env.py:109,135-148
+            self.observation_space = sp.Tuple((sp.Discrete(2), sp.Discrete(12), sp.MultiBinary((3, 3, 59))))
+            self.action_space = sp.Discrete(2)
+        else:                                              # two action dimensions reach the env
+            self.observation_space = sp.Box(low=0, high=1, shape=(7,), dtype=int)
+            self.action_space = sp.MultiDiscrete([4, 3])
+        self.calls = []
+        if takes_epoch:
+            self.reset = lambda epoch=None: self._reset(epoch)
+        else:
+            self.reset = lambda: self._reset("none")
+        self.stat = dict(success=1, steps_taken=9)
+
+    def _obs(self, odim):
+        import torch
+        return torch.arange(self.nenvs * self.n * odim, dtype=torch.float32).reshape(self.nenvs, self.n, -1)
+
+    def _reset(self, epoch):
+        self.calls.append(("reset", epoch))
+        return self._obs(self._odim)
+
+    def step(self, action):
+        self.calls.append(("step", action))
+        return self._obs(self._odim), "r", "d", dict(k=1)
+
+    def get_stat(self):
+        return dict(self.stat)
+
+
+@pytest.mark.parametrize("kind,odim,nact,dact", [("pp", 29 * 9, 5, 1), ("tj", 2 + 9 * 59, 2, 1), ("multi", 7, 4, 2)])
+def test_gym_wrapper_surface(kind, odim, nact, dact):
+    from ic3net_b200 import spaces
+    from ic3net_b200.env_wrappers import GymWrapper
+    env = _FakeEnv(spaces, kind, takes_epoch=(kind == "tj"))
+    env._odim = odim
+    w = GymWrapper(env)
+    assert (w.observation_dim, w.num_actions, w.dim_actions, w.nenvs) == (odim, nact, dact, 3)
+    assert w.action_space is env.action_space
+    obs = w.reset(7)
+    assert tuple(obs.shape) == (3, 4, odim)
+    assert env.calls[-1] == ("reset", 7 if kind == "tj" else "none")        # epoch only where reset() takes it
+    heads = ["head0", "head1"]
+    o, r, d, info = w.step(heads)
+    assert env.calls[-1] == ("step", "head0" if dact == 1 else heads)       # one action dim: only head 0 reaches the env
+    assert tuple(o.shape) == (3, 4, odim) and (r, d, info) == ("r", "d", dict(k=1))
+    assert w.get_stat() == dict(success=1) and env.stat["steps_taken"] == 9
+    assert np.array_equal(w.reward_terminal(), np.zeros(1))                  # env without reward_terminal()
+    env.reward_terminal = lambda: "rt"
+    assert w.reward_terminal() == "rt"
+    assert w._flatten_obs(obs).shape == obs.shape
+
+
+@pytest.mark.parametrize("kind", ["pp", "tj", "multi"])
+def test_gym_wrapper_matches_reference_properties(kind):
+    """observation_dim / num_actions / dim_actions against the reference's GymWrapper on the same space objects."""
+    from oracle import ref_shims
+    if not ref_shims.reference_available():
+        pytest.skip("reference checkout not present")
+    ref_shims.install()
+    import gym.spaces as gspaces                      # the stub installed by ref_shims
+    ref = _ref_module("env_wrappers")
+    from ic3net_b200.env_wrappers import GymWrapper
+    env = _FakeEnv(gspaces, kind)
+    a, b = GymWrapper(env), ref.GymWrapper(env)
+    assert (a.observation_dim, a.num_actions, a.dim_actions) == (b.observation_dim, b.num_actions, b.dim_actions)
