@@ -76,6 +76,8 @@ def build_parser():
     parser.add_argument('--obs_mode', default='index', choices=['index', 'dense'],
                         help='encoder fed from the env state (index) or from a materialised [B,N,O] observation (dense)')
     parser.add_argument('--policy_impl', default=None, choices=['tc', 'simt'], help='tcgen05 or fp32 SIMT policy kernels')
+    parser.add_argument('--grad_impl', default='autograd', choices=['autograd', 'manual'],
+                        help='compute_grad through torch autograd recompute (default) or the explicit backward formulas')
     parser.add_argument('--use_graph', action='store_true', default=False, help='replay the rollout as a CUDA graph')
     parser.add_argument('--rollout_only', action='store_true', default=False,
                         help='collect batches and statistics without the optimizer step')

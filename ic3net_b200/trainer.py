@@ -391,6 +391,8 @@ class Trainer(object):
         nw = (T + W - 1) // W
         dh = dc = None
         tot = dict(action_loss=0.0, value_loss=0.0, entropy=0.0)
+        if getattr(args, 'grad_impl', 'autograd') == 'manual':
+            return self._compute_grad_manual(adv, ret, W, nw)
         for k in reversed(range(nw)):
             t0, t1 = k * W, min(T, (k + 1) * W)
             h0 = b['ck_h'][k].clone().requires_grad_(True)
@@ -402,6 +404,37 @@ class Trainer(object):
             dh, dc = h0.grad.detach(), c0.grad.detach()
             for key in tot:
                 tot[key] += float(st[key].item())
+        return tot
+
+    def _compute_grad_manual(self, adv, ret, W, nw):
+        """``args.grad_impl == 'manual'``: the same gradient from the explicit backward formulas of bptt.py (no autograd
+        graph; validated in float64 against the oracle by tests/test_bptt_manual.py).  Opt-in until it has been
+        measured on the GPU."""
+        from . import bptt
+        b, net, args = self._buf, self.policy_net, self.args
+        B, N = self.env.env.nenvs, args.nagents
+        T = b['T']
+        P, G = {}, {}
+        for name, p in net.named_parameters():
+            if p.grad is None:
+                p.grad = torch.zeros_like(p)
+            P[name], G[name] = p.detach(), p.grad
+        spec = bptt.Spec(N, args.hid_size, len(args.naction_heads), bool(args.hard_attn) and bool(args.commnet),
+                         getattr(args, 'comm_mode', 'avg') == 'avg', bool(args.comm_mask_zero), args.value_coeff,
+                         args.entr, args.detach_gap, args.max_steps)
+        if self.is_tj:
+            obs_fn = lambda t: b['s_obs'][t].reshape(B * N, -1)
+        else:
+            obs_fn = lambda t: self._pp_sparse_obs(b['s_loc'][t])
+        rec = dict(fresh=b['s_fresh'], comm=b['s_comm'], alive=b['s_alive'], t_ep=b['s_tep'], action=b['action'],
+                   alive_post=b['ralive'], obs=obs_fn)
+        tot = dict(action_loss=0.0, value_loss=0.0, entropy=0.0)
+        dh = dc = None
+        for k in reversed(range(nw)):
+            t0, t1 = k * W, min(T, (k + 1) * W)
+            dh, dc, st = bptt.window_backward(P, G, spec, rec, t0, t1, b['ck_h'][k], b['ck_c'][k], adv, ret, dh, dc)
+            for key in tot:
+                tot[key] += st[key]
         return tot
 
     # only used when there is a single process (trainer.py:245-256)
