@@ -119,3 +119,33 @@ def test_sparse_observation_path_equals_dense():
     Gs, _ = _run_manual(args, meta, p, rec, adv, ret, 10, sparse=True)
     for key in Gd:
         assert torch.allclose(Gd[key], Gs[key], rtol=1e-11, atol=1e-13), key
+
+
+@pytest.mark.parametrize("dim,vision,n", [(5, 0, 3), (4, 1, 2), (6, 2, 5), (20, 1, 10)])
+def test_sparse_pp_observation_equals_oracle_observation(dim, vision, n):
+    """Trainer._pp_sparse_obs (the (index, value) form of the predator-prey observation both gradient paths consume)
+    scattered back to dense equals the oracle's observation, incl. stacked predators, prey under a predator and
+    windows that leave the grid.  Runs on CPU: the method only touches torch ops and four env attributes."""
+    from types import SimpleNamespace
+    from oracle.pp_env import PredatorPreyOracle
+    from ic3net_b200.trainer import Trainer
+    orc = PredatorPreyOracle(n, dim, vision)
+    rs = np.random.RandomState(dim * 10 + vision)
+    B = 6
+    loc = rs.randint(0, dim, size=(B, n + 1, 2))
+    loc[0, 1] = loc[0, 0]                      # two predators on one cell
+    loc[1, n] = loc[1, 0]                      # prey under a predator
+    loc[2, 0] = (0, 0)                         # window leaves the grid (vision > 0)
+    loc[3, :] = (dim - 1, dim - 1)             # everybody in one corner
+    fake = SimpleNamespace(env=SimpleNamespace(env=SimpleNamespace(dim=dim, vision=vision, npredator=n,
+                                                                   vocab_size=orc.vocab_size)))
+    idx, val = Trainer._pp_sparse_obs(fake, torch.tensor(loc, dtype=torch.int32))
+    O = orc.obs_dim
+    dense = torch.zeros(B * n, O, dtype=torch.float64)
+    dense.scatter_add_(1, idx, val.double())
+    for b in range(B):
+        orc.reset(locs=loc[b])
+        assert np.array_equal(dense[b * n:(b + 1) * n].numpy(), orc.flat_obs()), b
+    # and through the encoder of bptt.py: sparse form == dense form
+    P = {"encoder.weight": torch.randn(7, O, dtype=torch.float64), "encoder.bias": torch.randn(7, dtype=torch.float64)}
+    assert torch.allclose(bptt.encode(P, (idx, val.double())), bptt.encode(P, dense), rtol=1e-12, atol=1e-12)
