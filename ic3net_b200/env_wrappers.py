@@ -89,7 +89,7 @@ class GymWrapper(object):
         stat.pop('steps_taken', None)            # env_wrappers.py:102-104: the trainer counts steps itself
         return stat
 
-    # ---- rendering (curses in the reference; the batched envs print a text frame) ---------------------
+    # ---- rendering (curses in the reference; out of scope here: the batched envs raise NotImplementedError) ----
     def display(self):
         self.env.render()
 

@@ -179,3 +179,6 @@ class PredatorPreyEnv(object):
 
     def render(self, mode='human', close=False):
         raise NotImplementedError("curses rendering is not part of the accelerated path")
+
+    def exit_render(self):
+        raise NotImplementedError("curses rendering is not part of the accelerated path")

@@ -189,3 +189,6 @@ class TrafficJunctionEnv(object):
 
     def render(self, mode='human', close=False):
         raise NotImplementedError("curses rendering is not part of the accelerated path")
+
+    def exit_render(self):
+        raise NotImplementedError("curses rendering is not part of the accelerated path")
