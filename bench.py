@@ -98,25 +98,67 @@ def host_cores():
     return max(1, n)
 
 
+REF_NPROCESSES = 16      # BASELINE.json metric: "vs reference CPU nprocesses=16" (README.md:46-48), whatever the box has
+
+
+def ref_cfg(wl, batch_size=500):
+    """Flags of the reference run (main.py:25-109 names) for a workload."""
+    w = dict(WORKLOADS[wl])
+    w.pop("nenvs")
+    ic3 = w.pop("ic3net")
+    d = dict(hid_size=128, recurrent=True, rnn_type="LSTM", batch_size=batch_size, seed=1, lrate=1e-3)
+    d.update(w)
+    d.update(dict(ic3net=True) if ic3 else dict(commnet=True))
+    return d
+
+
+def run_reference(wl, modes, warmup, iters, nprocesses=REF_NPROCESSES, batch_size=500):
+    """The UNMODIFIED reference's MultiProcessTrainer (oracle/ref_baseline.py) in a fresh interpreter."""
+    cfg = dict(args=ref_cfg(wl, batch_size), nprocesses=nprocesses, modes=modes, warmup=warmup, iters=iters)
+    env = dict(os.environ, OMP_NUM_THREADS="1", MKL_NUM_THREADS="1", PYTHONWARNINGS="ignore")
+    out = subprocess.check_output([sys.executable, "-m", "oracle.ref_baseline", json.dumps(cfg)], cwd=ROOT, env=env,
+                                  stderr=subprocess.DEVNULL)
+    return json.loads(out.decode().strip().split("\n")[-1])
+
+
+def ref_rate(samples, nagents):
+    steps = sum(x[0] for x in samples)
+    secs = sum(x[1] for x in samples)
+    return steps * nagents / secs, secs
+
+
 def reference_arm(opts):
+    """CPU baseline of record: the reference's own multi_processing.py path at nprocesses = 16, OMP_NUM_THREADS = 1,
+    float64, on this box's host cores.  A "step" is one update call of its MultiProcessTrainer with compute_grad
+    patched out, i.e. run_batch in all 16 workers (batch_size 500 env steps each) -- the like-for-like of the GPU
+    arm's rollout metric; the full train_batch (rollout + backward + gradient sum + RMSprop) is timed beside it."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
     cores = host_cores()
     K, W = opts.steps, opts.warmup
-    budget = max(0.5, min(15.0, 90.0 / max(1, K + W)))   # each "step" = one bounded sample; whole run ends in minutes
-    r = run_cpu(opts.workload, cores, budget, W + K)
-    vals = r["samples"][W:]
-    secs = sum(x[1] for x in vals)
-    v = sum(x[0] for x in vals) * WORKLOADS[opts.workload]["nagents"] / secs
     a = make_args(opts.workload)
+    N = a.nagents
+    r = run_reference(opts.workload, ["rollout"], W, K)
+    samples = r["modes"]["rollout"]["samples"][W:]
+    v, secs = ref_rate(samples, N)
+    rt = run_reference(opts.workload, ["train_batch"], 1, 3)
+    vt, _ = ref_rate(rt["modes"]["train_batch"]["samples"][1:], N)
+    port = run_cpu(opts.workload, REF_NPROCESSES, 4.0)
+    sample = ("%d processes (reference MultiProcessTrainer, unmodified, float64, OMP_NUM_THREADS=1) x %d run_batch "
+              "calls of batch_size 500 env steps each" % (REF_NPROCESSES, K))
     line = dict(metric=METRIC, value=v, unit="agent-env-steps/s", n_gpus=opts.gpus, steps=K, warmup=W,
                 ms_per_step=1e3 * secs / K, higher_is_better=True, scaling="weak",
                 vs_baseline=None, dtype="f64", data="synthetic", impl="reference",
-                config=dict(workload=opts.workload, envs_per_process=1, nagents=a.nagents, max_steps=a.max_steps),
-                cpu_baseline=dict(value=v, unit="agent-env-steps/s", cores=cores, kind="port",
-                                  sample="%d processes x %.1f s of oracle get_episode loops (1 env each, float64, "
-                                         "OMP_NUM_THREADS=1) per step" % (cores, budget)),
+                config=dict(workload=opts.workload, nprocesses=REF_NPROCESSES, envs_per_process=1, nagents=N,
+                            max_steps=a.max_steps, batch_size=500, host_cores=cores),
+                cpu_baseline=dict(value=v, unit="agent-env-steps/s", cores=min(cores, REF_NPROCESSES),
+                                  nprocesses=REF_NPROCESSES, kind="reference", sample=sample),
+                train_batch=dict(value=vt, unit="agent-env-steps/s",
+                                 sample="3 full train_batch calls after 1 warm-up (rollout + compute_grad + gradient "
+                                        "sum over the 16 workers + RMSprop)"),
+                port=dict(value=port["value"], unit="agent-env-steps/s", nprocesses=REF_NPROCESSES, kind="port",
+                          sample="oracle restatement of get_episode, %d processes x 4 s" % REF_NPROCESSES),
                 e2e=dict(value=v, unit="agent-env-steps/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0),
                 gpu_launches=0)
     print(json.dumps(line))
@@ -182,6 +224,7 @@ class ClockSampler(object):
 # ------------------------------------------------------------------------------
 def gpu_arm(opts):
     import ctypes as C
+    import statistics
 
     import numpy as np
     import torch
@@ -190,6 +233,7 @@ def gpu_arm(opts):
     from ic3net_b200 import _lib, data
     from ic3net_b200.action_utils import parse_action_args, select_action
     from ic3net_b200.comm import CommNetMLP
+    from ic3net_b200.multi_gpu import MultiGPUTrainer
     from ic3net_b200.trainer import Trainer
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -207,10 +251,12 @@ def gpu_arm(opts):
         dist.init_process_group("nccl", device_id=dev)
     K, W = opts.steps, max(3, opts.warmup)
 
-    def build(obs_mode, nenvs=None):
+    def build(obs_mode, nenvs=None, **extra):
         a = make_args(opts.workload, rank, obs_mode, nenvs)
         a.policy_impl = opts.policy_impl
         a.obs_chunk_mb = opts.obs_chunk_mb
+        for k, v in extra.items():
+            setattr(a, k, v)
         env = data.init(a.env_name, a)
         a.num_inputs = env.observation_dim
         a.num_actions = [env.num_actions] + ([2] if a.hard_attn else [])
@@ -221,75 +267,132 @@ def gpu_arm(opts):
         return a, env, net, Trainer(a, net, env)
 
     a, env, net, tr = build(opts.obs_mode)
+    mgt = MultiGPUTrainer(a, lambda: tr)                      # broadcasts rank 0's parameters (no-op at N = 1)
     B, N, H, O = a.nenvs, a.nagents, a.hid_size, a.num_inputs
-    nparam = sum(p.numel() for n_, p in net.named_parameters() if not n_.startswith("hidd_encoder"))
-    grad_flat = torch.zeros(nparam + 64, device=dev)       # REINFORCE gradient + packed stat scalars
-
     chunk = a.max_steps                                      # record buffers hold one episode horizon
+    use_graph = not opts.no_graph
 
-    graphs, graph_launches, replayed = {}, {}, [0]
+    class Runner(object):
+        """K lock-step iterations of a trainer, eagerly or as CUDA-graph replays (one graph per distinct length)."""
 
-    def enqueue(trn, steps):
-        done = 0
-        while done < steps:                                  # episode-horizon chunks reuse the record buffers
-            n = min(chunk, steps - done)
-            if opts.graph and n == chunk and id(trn) in graphs:
-                graphs[id(trn)].replay()                     # one CUDA-graph launch per episode horizon
-                replayed[0] += graph_launches[id(trn)]
-            else:
-                trn._enqueue(n)
-            done += n
+        def __init__(self, trn):
+            self.trn, self.graphs, self.replayed = trn, {}, 0
 
-    def capture(trn):
-        """Capture one episode horizon of the rollout (all kernels of `chunk` lock-step iterations) once."""
+        def _capture(self, n):
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            l0 = _lib.launch_count()
+            with torch.cuda.graph(g):
+                self.trn._enqueue(n)
+            self.graphs[n] = (g, _lib.launch_count() - l0)
+
+        def warm(self, steps):
+            self.trn._alloc(chunk)
+            e = self.trn.env.env
+            e.reset(want_obs=False) if self.trn.args.env_name == "predator_prey" else e.reset(0, want_obs=False)
+            self.trn.policy_net.packed()
+            self.trn._enqueue(max(3, steps))                 # eager warm-up (lazy attributes, allocator, table)
+            if use_graph:
+                done = 0
+                while done < K:
+                    n = min(chunk, K - done)
+                    if n not in self.graphs:
+                        self._capture(n)
+                    done += n
+                self.enqueue(K)                              # one replayed pass before anything is timed
+            torch.cuda.synchronize()
+
+        def enqueue(self, steps):
+            done = 0
+            while done < steps:                              # episode-horizon chunks reuse the record buffers
+                n = min(chunk, steps - done)
+                if use_graph and n in self.graphs:
+                    self.graphs[n][0].replay()               # one launch per chunk
+                    self.replayed += self.graphs[n][1]
+                else:
+                    self.trn._enqueue(n)
+                done += n
+
+        def launches(self):
+            return _lib.launch_count() + self.replayed
+
+    def timed_region(run, steps, reduce_stats):
+        """ONE timed region: K lock-step iterations + what a data-parallel update does with a rollout-only batch
+        (main.py --rollout_only): the batch statistics reduced on the device and, for N > 1, the REAL collectives of
+        MultiGPUTrainer -- all-reduce of the flat gradient buffer (FlatRMSprop.flat_grads, multi_processing.py:90-95)
+        and of the float64 statistics vector -- then the one device->host copy of the merged statistics.
+        Bracketed by barrier + synchronize on both sides; device time from CUDA events."""
+        if world > 1:
+            dist.barrier()
         torch.cuda.synchronize()
-        g = torch.cuda.CUDAGraph()
-        l0 = _lib.launch_count()
-        with torch.cuda.graph(g):
-            trn._enqueue(chunk)
-        graphs[id(trn)] = g
-        graph_launches[id(trn)] = _lib.launch_count() - l0   # kernels inside one replay
-
-    def timed_rollout(trn, steps):
-        """Enqueue `steps` lock-step iterations (+ the per-update gradient all-reduce); device events."""
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        w0 = time.time()
         e0.record()
-        enqueue(trn, steps)
-        if world > 1:
-            dist.all_reduce(grad_flat)                       # one collective per update (multi_processing.py:90-95)
+        run.enqueue(steps)
+        if reduce_stats:
+            stat = mgt.reduce_device(None, with_grads=True)
         e1.record()
-        return e0, e1
+        torch.cuda.synchronize()
+        w1 = time.time()
+        if world > 1:
+            dist.barrier()
+        t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()), (w0, w1)
 
-    # ---- warm-up + timed region (value: inputs resident in HBM, no host sync inside) ----
-    tr._alloc(chunk)
-    env.env.reset(want_obs=False) if a.env_name == "predator_prey" else env.env.reset(0, want_obs=False)
-    enqueue(tr, W)
-    if opts.graph:
-        capture(tr)
-        enqueue(tr, chunk)
-    if world > 1:
-        dist.all_reduce(grad_flat)
-    torch.cuda.synchronize()
-    launches0 = _lib.launch_count() + replayed[0]
+    def measure(run, reduce_stats=True, min_seconds=0.5, max_repeats=400):
+        """Repeat the K-step region until >= min_seconds of device time have been measured (at least 3 times):
+        the driver's K = 20 is an 11 ms region, too short for one number to mean anything.  Every region time is
+        already the max over ranks, so all ranks leave the loop together."""
+        times, windows, total = [], [], 0.0
+        while (total < min_seconds * 1e3 or len(times) < 3) and len(times) < max_repeats:
+            ms, win = timed_region(run, K, reduce_stats)
+            times.append(ms)
+            windows.append(win)
+            total += ms
+        return times, (windows[0][0], windows[-1][1])
+
+    # ---- warm-up + timed regions (value: inputs resident in HBM, no host sync before the statistics copy) ----
+    run = Runner(tr)
+    run.warm(W)
+    launches0 = run.launches()
     with ClockSampler(local) as clk:
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-        wall0 = time.time()
-        e0, e1 = timed_rollout(tr, K)
-        torch.cuda.synchronize()
-        wall1 = time.time()
-        if world > 1:
-            dist.barrier()
-        ms = e0.elapsed_time(e1)
+        times, window = measure(run)
         time.sleep(0.2)
-    launches = _lib.launch_count() + replayed[0] - launches0
-    t = torch.tensor([ms], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms = float(t.item())
-    tr.collect_stat()                                         # raises on any device-side error flag
+    launches = (run.launches() - launches0) // max(1, len(times))
+    ms = statistics.median(times)
     value = world * B * N * K / (ms * 1e-3)
+    timing = dict(repeats=len(times), ms_median=ms, ms_min=min(times), ms_max=max(times),
+                  region="K lock-step iterations + device stat reduction"
+                         + (" + all-reduce(flat_grads) + all-reduce(stat vector)" if world > 1 else "")
+                         + " + 1 D2H stat copy; value uses the median region")
+
+    # ---- full training update: MultiGPUTrainer.train_batch on every rank (rollout with the reference batch boundary
+    #      + compute_grad + gradient / statistics all-reduce + RMSprop), SURVEY 8(f)-1/2 + 8(e) ----
+    train = None
+    if not opts.quick and opts.train_updates > 0:
+        train = train_leg(opts, build, MultiGPUTrainer, world, dev, dist, torch)
+
+    # ---- e2e: the public, reference-shaped API with host-side actions / rewards, on EVERY rank ----
+    e2e = None
+    if not opts.quick:
+        if world > 1:
+            dist.barrier()
+        mine = e2e_loop(a, env, net, min(max(K, 50), 200), np, torch, select_action)
+        if world > 1:
+            agg = torch.tensor([mine["seconds"], float(mine["steps"])], device=dev, dtype=torch.float64)
+            mx = agg.clone()
+            dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+            sm = agg.clone()
+            dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+            total_steps, max_secs = float(sm[1].item()), float(mx[0].item())
+            mine = dict(mine, value=total_steps * B * N / max_secs, rank0_value=mine["value"],
+                        scope="all %d ranks ran the loop concurrently; value = total agent-env-steps / max wall time "
+                              "over ranks" % world,
+                        h2d_bytes_per_step=mine["h2d_bytes_per_step"] * world,
+                        d2h_bytes_per_step=mine["d2h_bytes_per_step"] * world)
+        e2e = mine
 
     line = None
     if rank == 0:
@@ -299,6 +402,7 @@ def gpu_arm(opts):
         except Exception:
             pass
         hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+        tc_peak = float(peaks.get("bf16_tflops", 2250.0))
         peak_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
 
         # ---- per-kernel device times (separate pass, CUDA events around every launch) ----
@@ -306,83 +410,143 @@ def gpu_arm(opts):
         is_pp = a.env_name == "predator_prey"
         state_bytes = 32 if is_pp else 64
         obs_bytes = (4 * O + state_bytes) * B * N             # obs written once + state/action/reward
+        ncu = {}
+        try:
+            ncu = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json"))).get(opts.workload, {})
+        except Exception:
+            pass
         roof = None
         if "obs_gather" in kern:
             ach = obs_bytes / (kern["obs_gather"] * 1e-3) / 1e9
-            traffic = None          # DRAM bytes per launch from the committed ncu --set full capture, when there is one
-            try:
-                traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))[opts.workload]["obs_gather"]
-            except Exception:
-                pass
             roof = dict(kernel="obs_gather", bound="hbm", achieved=ach, peak=hbm_peak, unit="GB/s",
-                        frac=ach / hbm_peak, traffic=traffic, peak_source=peak_src,
+                        frac=ach / hbm_peak, traffic=ncu.get("obs_gather"), peak_source=peak_src,
                         algorithmic_bytes_per_launch=obs_bytes, avg_launch_ms=kern["obs_gather"])
         kinfo = {}
         for k, v in kern.items():
             kinfo[k] = dict(avg_ms=v)
+        roof_enc = None
         if "encoder_dense" in kern:
             eb = (4 * O + 4 * H) * B * N
-            kinfo["encoder_dense"].update(bytes=eb, gbs=eb / (kern["encoder_dense"] * 1e-3) / 1e9,
-                                          hbm_frac=eb / (kern["encoder_dense"] * 1e-3) / 1e9 / hbm_peak)
+            ach = eb / (kern["encoder_dense"] * 1e-3) / 1e9
+            roof_enc = dict(kernel="encoder_dense", bound="hbm", achieved=ach, peak=hbm_peak, unit="GB/s",
+                            frac=ach / hbm_peak, traffic=ncu.get("encoder_dense"), algorithmic_bytes_per_launch=eb,
+                            avg_launch_ms=kern["encoder_dense"])
+        roof_tc = None
         if "policy_step" in kern:
             fl = (2 * H * H + 16 * H * H) * B * N
             pb = (20 * H + 4 * (sum(a.naction_heads) + 1) + 8) * B * N
             kinfo["policy_step"].update(flops=fl, tflops=fl / (kern["policy_step"] * 1e-3) / 1e12, bytes=pb,
                                         gbs=pb / (kern["policy_step"] * 1e-3) / 1e9,
-                                        math="tcgen05 kind::f16 hi/lo split, fp32 accumulate (prep + lstm_tc + heads)"
+                                        math="tcgen05 kind::f16 hi/lo split, fp32 accumulate"
                                         if net.policy_impl == "tc" else "fp32 SIMT (policy v1)")
+            if net.policy_impl == "tc" and "lstm_tc" in kern:
+                alg = fl / (kern["lstm_tc"] * 1e-3) / 1e12
+                roof_tc = dict(kernel="lstm_tc", bound="tensor", achieved=alg, issued=3 * alg, peak=tc_peak,
+                               unit="TFLOP/s", frac=alg / tc_peak, frac_issued=3 * alg / tc_peak,
+                               algorithmic_flops_per_launch=fl, avg_launch_ms=kern["lstm_tc"],
+                               note="1x algorithmic flops (SURVEY 8(d)); the fp16 hi/lo split issues 3 MMAs per "
+                                    "product; peak = measured dense bf16 cuBLAS",
+                               ncu_pipe_tensor_active_pct=ncu.get("lstm_tc_pipe_tensor_pct"),
+                               traffic=ncu.get("lstm_tc"))
 
-        # ---- fused index-form rollout (no [B,N,O] tensor) as a second data point ----
+        # ---- fused index-form rollout (no [B,N,O] tensor): the mode the trainer uses by default ----
         alt = None
         if opts.obs_mode == "dense" and world == 1 and not opts.quick:
             a2, env2, net2, tr2 = build("index")
-            tr2._alloc(chunk)
-            env2.env.reset(want_obs=False) if is_pp else env2.env.reset(0, want_obs=False)
-            enqueue(tr2, W)
-            if opts.graph:
-                capture(tr2)
-                enqueue(tr2, chunk)
-            torch.cuda.synchronize()
-            f0, f1 = timed_rollout(tr2, K)
-            torch.cuda.synchronize()
-            ms2 = f0.elapsed_time(f1)
-            alt = dict(obs_mode="index", value=B * N * K / (ms2 * 1e-3), ms_per_step=ms2 / K,
-                       note="same rollout with the encoder evaluated from the env state (bit-identical x)")
-            del tr2, net2, env2
-
-        # ---- e2e: the public, reference-shaped API with host-side actions / rewards ----
-        # (runs on rank 0 only -- this whole block does; for N > 1 the number is that rank's GPU driven through
-        #  the public API while the other ranks wait, and says so)
-        e2e = None if opts.quick else e2e_loop(a, env, net, min(K, 200), np, torch, select_action)
-        if e2e and world > 1:
-            e2e["scope"] = "rank 0 only (one GPU of the %d); ranks are independent replicas of this loop" % world
+            run2 = Runner(tr2)
+            run2.warm(W)
+            t2, _ = measure(run2, reduce_stats=False, min_seconds=0.25)
+            ms2 = statistics.median(t2)
+            alt = dict(obs_mode="index", value=B * N * K / (ms2 * 1e-3), ms_per_step=ms2 / K, repeats=len(t2),
+                       note="same rollout with the encoder evaluated from the env state (bit-identical x); "
+                            "this is Trainer's default obs_mode")
+            del tr2, net2, env2, run2
 
         # ---- CPU baseline (bounded sample of the same workload on the host cores) ----
         cores = host_cores()
-        cpu = run_cpu(opts.workload, cores, 12.0) if (world == 1 and not opts.quick) else None
+        cpu = None
+        if world == 1 and not opts.quick:
+            try:
+                r = run_reference(opts.workload, ["rollout"], 1, 4)
+                v, secs = ref_rate(r["modes"]["rollout"]["samples"][1:], N)
+                cpu = dict(value=v, unit="agent-env-steps/s", cores=min(cores, REF_NPROCESSES),
+                           nprocesses=REF_NPROCESSES, kind="reference",
+                           sample="reference MultiProcessTrainer (unmodified, float64, OMP_NUM_THREADS=1), %d processes "
+                                  "x 4 run_batch calls of 500 env steps after 1 warm-up (%.1f s)" % (REF_NPROCESSES, secs))
+            except Exception as ex:                           # staged reference missing: fall back to the port, say so
+                r = run_cpu(opts.workload, REF_NPROCESSES, 8.0)
+                cpu = dict(value=r["value"], unit="agent-env-steps/s", cores=min(cores, REF_NPROCESSES),
+                           nprocesses=REF_NPROCESSES, kind="port",
+                           sample="oracle restatement, %d processes x 8 s (reference copy unavailable: %s)"
+                                  % (REF_NPROCESSES, type(ex).__name__))
 
         line = dict(metric=METRIC, value=value, unit="agent-env-steps/s", n_gpus=world, steps=K, warmup=W,
                     ms_per_step=ms / K, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32",
                     data="synthetic",
                     config=dict(workload=opts.workload, envs_per_gpu=B, nagents=N, obs_dim=O, hid_size=H,
-                                max_steps=a.max_steps, obs_mode=opts.obs_mode, parallelism="dp%d" % world,
-                                cuda_graph=bool(opts.graph), policy_impl=net.policy_impl,
+                                max_steps=a.max_steps, obs_mode=opts.obs_mode, trainer_default_obs_mode="index",
+                                parallelism="dp%d" % world, cuda_graph=bool(use_graph), policy_impl=net.policy_impl,
                                 l2="per-step working set %.2f GB > 126 MB L2 (inputs larger than L2)"
                                    % ((8 * O + 20 * H) * B * N / 1e9),
-                                obs_chunks=(len(tr._dense_chunks(net.policy_cfg(B))) if opts.obs_mode == "dense" else 0),
                                 weights="random init (torch.manual_seed(0)), reference architecture"),
-                    clocks=clk.summary((wall0, wall1)), gpu_launches=launches, e2e=e2e, roofline=roof, kernels=kinfo)
+                    timing=timing, clocks=clk.summary(window), gpu_launches=launches, e2e=e2e, roofline=roof,
+                    roofline_encoder_dense=roof_enc, roofline_tensor=roof_tc, kernels=kinfo)
+        if train:
+            line["train_batch"] = train
         if alt:
             line["fused_index_rollout"] = alt
         if cpu:
-            line["cpu_baseline"] = dict(value=cpu["value"], unit="agent-env-steps/s", cores=cores, kind="port",
-                                        sample="%d processes x 12 s of oracle get_episode loops (1 env each, "
-                                               "float64, OMP_NUM_THREADS=1)" % cores)
+            line["cpu_baseline"] = cpu
         print(json.dumps(line))
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
     return 0
+
+
+def train_leg(opts, build, MultiGPUTrainer, world, dev, dist, torch):
+    """agent-env-steps/s of complete training updates: every rank runs MultiGPUTrainer.train_batch (rollout with
+    the reference batch boundary, compute_grad, ONE all-reduce of the flat gradient buffer + the statistics vector,
+    RMSprop) -- the like-for-like of the reference's MultiProcessTrainer.train_batch."""
+    a, env, net, tr = build("index", opts.train_envs or None, record_for_grad=True, batch_size=opts.train_batch_size,
+                            grad_impl=opts.grad_impl, value_coeff=0.01, entr=0.0, gamma=1.0, normalize_rewards=False,
+                            detach_gap=10000, grad_window=opts.grad_window)
+    mgt = MultiGPUTrainer(a, lambda: tr)
+    N = a.nagents
+    mgt.train_batch(0)                                        # warm-up (allocations, graph-free)
+    torch.cuda.synchronize()
+    times, steps, phases = [], 0, []
+    for u in range(opts.train_updates):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        stat = mgt.train_batch(u + 1)
+        e1.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        times.append(float(t.item()))
+        steps += int(stat["num_steps"])                       # already summed over ranks
+    # split of one update on this rank: rollout alone vs the rest
+    torch.cuda.synchronize()
+    T, quota = tr.batch_plan()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    tr.rollout(T, 0, quota=quota)
+    e1.record()
+    torch.cuda.synchronize()
+    roll_ms = e0.elapsed_time(e1)
+    tot_ms = sum(times)
+    return dict(value=steps * N / (tot_ms * 1e-3), unit="agent-env-steps/s", updates=opts.train_updates,
+                envs_per_gpu=a.nenvs, batch_size=a.batch_size, lock_steps_per_update=T,
+                ms_per_update=tot_ms / opts.train_updates, rollout_ms=roll_ms,
+                grad_reduce_step_ms=tot_ms / opts.train_updates - roll_ms, grad_impl=opts.grad_impl,
+                replica_max_abs_diff=mgt.replica_checksum(), collectives_per_update=mgt.collectives / max(1, opts.train_updates + 1)
+                if world > 1 else 0,
+                api="MultiGPUTrainer.train_batch (all ranks; device time, max over ranks)")
 
 
 def per_kernel_times(tr, a, env, net, steps, C, torch, _lib):
@@ -397,7 +561,7 @@ def per_kernel_times(tr, a, env, net, steps, C, torch, _lib):
     is_tj = a.env_name == "traffic_junction"
     hard = int(bool(a.hard_attn))
     nh = len(a.naction_heads)
-    ev = {}
+    ev, split = {}, {}
 
     def timed(name, fn):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -437,6 +601,11 @@ def per_kernel_times(tr, a, env, net, steps, C, torch, _lib):
                            action=b["action"][t].data_ptr(), workspace=_lib.ptr(ws),
                            err=b["err"].data_ptr(), **src)
         timed("policy_step", lambda: lib.ic3_policy_step(C.byref(cfg), C.byref(w), C.byref(io), s))
+        if net.policy_impl == "tc" and t >= steps - 4:        # split of the last few steps (extra passes, same state)
+            ms3 = (C.c_float * 3)()
+            _lib.check(lib.ic3_policy_step_profile(C.byref(cfg), C.byref(w), C.byref(io), s, ms3))
+            for nm, v in zip(("prep", "lstm_tc", "heads_finish"), ms3):
+                split.setdefault(nm, []).append(float(v))
         r = _lib.RolloutIO(t=t, max_steps=a.max_steps, nheads=nh, hard_attn=hard,
                            comm_action_one=int(bool(a.comm_action_one)), last=0, action=b["action"][t].data_ptr(),
                            t_ep=b["t_ep"].data_ptr(), fresh=b["fresh"].data_ptr(), comm_next=b["comm"].data_ptr(),
@@ -454,7 +623,9 @@ def per_kernel_times(tr, a, env, net, steps, C, torch, _lib):
                                                       b["step_reward"].data_ptr(), None, b["err"].data_ptr(),
                                                       C.byref(r), s))
     torch.cuda.synchronize()
-    return {k: sum(x.elapsed_time(y) for x, y in v) / len(v) for k, v in ev.items()}
+    out = {k: sum(x.elapsed_time(y) for x, y in v) / len(v) for k, v in ev.items()}
+    out.update({k: sum(v) / len(v) for k, v in split.items()})
+    return out
 
 
 def e2e_loop(a, env, net, steps, np, torch, select_action):
@@ -536,7 +707,7 @@ def e2e_loop(a, env, net, steps, np, torch, select_action):
     per_step.sort()
     ms1 = torch.cuda.memory_stats()
     e.err.zero_()
-    return dict(value=B * N * steps / dt, unit="agent-env-steps/s", h2d_bytes_per_step=h2d // steps,
+    return dict(value=B * N * steps / dt, unit="agent-env-steps/s", seconds=dt, h2d_bytes_per_step=h2d // steps,
                 d2h_bytes_per_step=d2h // steps, steps=steps, ms_per_step=1e3 * dt / steps,
                 phases_ms={k: round(1e3 * v / steps, 4) for k, v in phases.items()},
                 step_ms_median=round(1e3 * per_step[len(per_step) // 2], 4), step_ms_max=round(1e3 * per_step[-1], 4),
@@ -556,7 +727,15 @@ def main():
     ap.add_argument("--obs_mode", default="dense", choices=["dense", "index"])
     ap.add_argument("--policy_impl", default=None, choices=["tc", "simt"],
                     help="tcgen05 tensor-core policy kernels (default for hid_size 128) or the fp32 SIMT kernel")
-    ap.add_argument("--graph", action="store_true", help="replay each episode horizon of the rollout as one CUDA graph")
+    ap.add_argument("--no_graph", action="store_true",
+                    help="enqueue every kernel of the rollout eagerly (default: CUDA-graph replay of the K-step region, "
+                         "what Trainer(use_graph=True) does; removes the host launch skew between ranks)")
+    ap.add_argument("--graph", action="store_true", help="(default now; kept for old command lines)")
+    ap.add_argument("--train_updates", type=int, default=2, help="timed MultiGPUTrainer.train_batch updates (0 = skip)")
+    ap.add_argument("--train_envs", type=int, default=0, help="env slots per GPU of the train_batch leg (0 = workload's)")
+    ap.add_argument("--train_batch_size", type=int, default=500, help="--batch_size of the train_batch leg (reference default)")
+    ap.add_argument("--grad_impl", default="autograd", choices=["autograd", "manual", "kernels"])
+    ap.add_argument("--grad_window", type=int, default=40)
     ap.add_argument("--quick", action="store_true", help="skip the e2e / index / CPU legs (profiling runs)")
     ap.add_argument("--obs_chunk_mb", type=float, default=0.0,
                     help="dense rollout: gather + encode observations in chunks of env slots of at most this size "

@@ -138,6 +138,8 @@ def window_backward(P, G, spec, rec, t0, t1, h0, c0, adv, ret, dh_in=None, dc_in
             dh = dh + dv.unsqueeze(1) * P["value_head.weight"]
             # action heads
             lp_taken = torch.zeros(R, dtype=dt, device=h.device)
+            # slots that already completed their batch (trainer.py:231) contribute nothing, not even entropy
+            vrow = rec["valid"][t].to(dt).repeat_interleave(N).unsqueeze(1) if "valid" in rec else 1.0
             for m in range(spec.nheads):
                 Wm, bm = P["heads.%d.weight" % m], P["heads.%d.bias" % m]
                 logp = torch.log_softmax(h2 @ Wm.t() + bm, dim=-1)
@@ -146,10 +148,10 @@ def window_backward(P, G, spec, rec, t0, t1, h0, c0, adv, ret, dh_in=None, dc_in
                 lp_taken += logp.gather(-1, am).squeeze(-1)
                 onehot = torch.zeros_like(pm).scatter_(-1, am, 1.0)
                 dlogit = (-A * alive_post).unsqueeze(1) * (onehot - pm)
-                ent -= (logp * pm).sum()
+                ent -= (logp * pm * vrow).sum()
                 if spec.entr > 0:
                     Hm = -(pm * logp).sum(-1, keepdim=True)
-                    dlogit = dlogit + spec.entr * pm * (logp + Hm)
+                    dlogit = dlogit + spec.entr * pm * (logp + Hm) * vrow
                 G["heads.%d.weight" % m] += dlogit.t() @ h2
                 G["heads.%d.bias" % m] += dlogit.sum(0)
                 dh = dh + dlogit @ Wm

@@ -1313,6 +1313,38 @@ int ic3_tc_pack(const ic3_policy_cfg* cfg, const ic3_policy_params* p, const ic3
   return IC3_OK;
 }
 
+// Per-kernel timing hook (ic3_policy_step_profile): when set, events are recorded on the stream before the first
+// kernel of the step and after each of its kernels.  Host-side only; nullptr in normal operation.
+static cudaEvent_t* g_prof_ev = nullptr;
+static inline void prof_mark(int i, cudaStream_t s) {
+  if (g_prof_ev) cudaEventRecord(g_prof_ev[i], s);
+}
+
+extern "C" int ic3_policy_step_profile(const ic3_policy_cfg* cfg, const ic3_policy_packed* w, const ic3_policy_io* io,
+                                       void* stream, float* ms) {
+  static cudaEvent_t ev[4];
+  static bool made = false;
+  if (!ms) return IC3_E_NULL;
+  if (!made) {
+    for (int i = 0; i < 4; ++i) {
+      cudaError_t e = cudaEventCreate(&ev[i]);
+      if (e != cudaSuccess) return (int)e;
+    }
+    made = true;
+  }
+  g_prof_ev = ev;
+  const int rc = ic3_policy_step(cfg, w, io, stream);
+  g_prof_ev = nullptr;
+  if (rc) return rc;
+  cudaError_t e = cudaEventSynchronize(ev[3]);
+  if (e != cudaSuccess) return (int)e;
+  for (int i = 0; i < 3; ++i) {
+    e = cudaEventElapsedTime(&ms[i], ev[i], ev[i + 1]);
+    if (e != cudaSuccess) return (int)e;
+  }
+  return IC3_OK;
+}
+
 int ic3_tc_policy_step(const ic3_policy_cfg* cfg, const ic3_policy_packed* w, const ic3_policy_io* io, cudaStream_t s) {
   if (cfg->H != TC_H) return IC3_E_UNSUPPORTED;
   if (!io->workspace || !w->lstm_img || !w->bias_cat) return IC3_E_NULL;
@@ -1327,6 +1359,7 @@ int ic3_tc_policy_step(const ic3_policy_cfg* cfg, const ic3_policy_packed* w, co
   src.split = cfg->obs_vocab > 0;
   src.table = io->x_table;
   if (src.table && !src.split) return IC3_E_RANGE;      // the table IS the first of the two sums
+  prof_mark(0, s);
   if (io->x) {
     IC3_LAUNCH_RC(ic3_launch_pdl(prep_kernel<XSRC_TENSOR, false>, dim3(2 * ntiles_pad), dim3(256), 0, s, *cfg, *io, img, src));
   } else if (io->pp_env && io->pp_state) {       // fused index encoder, predator-prey
@@ -1368,6 +1401,7 @@ int ic3_tc_policy_step(const ic3_policy_cfg* cfg, const ic3_policy_packed* w, co
   } else {
     return IC3_E_NULL;
   }
+  prof_mark(1, s);
   const size_t smem = NSTAGE_P * STAGE_BYTES + 256 + TC_H * HEAD_PAD * sizeof(float) + 4 * TC_H * sizeof(float);
   int nout = 1;
   for (int k = 0; k < cfg->nheads; ++k) nout += cfg->head_dim[k];
@@ -1384,9 +1418,11 @@ int ic3_tc_policy_step(const ic3_policy_cfg* cfg, const ic3_policy_packed* w, co
     case 8: rc = launch_lstm<8>(cfg, io, w, img, ntiles_pad, smem, nout, partial, s); break;
   }
   if (rc) return rc;
+  prof_mark(2, s);
   if (fused_heads) {
     IC3_LAUNCH_RC(ic3_launch_pdl(heads_finish_kernel, dim3((unsigned)((R + 127) / 128)), dim3(128), 0, s, *cfg, *w, *io,
                                  (const float*)partial));
+    prof_mark(3, s);
     return IC3_OK;
   }
   const int P = nout <= 8 ? 8 : (nout <= 16 ? 16 : 32);
@@ -1396,5 +1432,6 @@ int ic3_tc_policy_step(const ic3_policy_cfg* cfg, const ic3_policy_packed* w, co
   else if (P == 16) heads_kernel<16><<<hgrid, 256, 0, s>>>(*cfg, *w, *io);
   else heads_kernel<32><<<hgrid, 256, 0, s>>>(*cfg, *w, *io);
   IC3_LAUNCH_CHECK();
+  prof_mark(3, s);
   return IC3_OK;
 }

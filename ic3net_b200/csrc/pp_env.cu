@@ -131,7 +131,9 @@ __global__ void pp_step_kernel(PPArgs a, const int32_t* __restrict__ act, int ac
       cc = l[1];
     }
     if (lane < N) rch = a.st.reached[(size_t)e * N + lane];
-    if (do_step) {
+    if (do_step && r.has && ic3_rollout_halted(r.io, e, a.cfg.B, N, lane)) {
+      // this slot has completed its batch (trainer.py:231): nothing moves, null records
+    } else if (do_step) {
       if (a.st.done[e]) {  // :129-130 RuntimeError("Episode is done")
         if (lane == 0) atomicOr(err, IC3_ERR_EPISODE_DONE);
       } else {

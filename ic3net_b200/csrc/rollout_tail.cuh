@@ -16,6 +16,25 @@ static inline RolloutOpt make_rollout_opt(const ic3_rollout_io* r) {
   return o;
 }
 
+// Reference batch boundary (trainer.py:231-237): a worker plays whole episodes until it holds >= batch_size steps,
+// so its last episode overshoots.  With r.batch_size > 0 a slot HALTS at the first episode end at which its step
+// count has reached batch_size; from then on the lock-step iterations skip it: no env step, no statistics, null
+// records (rec_valid = 0, alive = 0, reward = 0, episode_mask = 0).  Returns true for a halted slot.
+__device__ __forceinline__ bool ic3_rollout_halted(const ic3_rollout_io& r, int e, int B, int N, int lane) {
+  if (r.batch_size <= 0 || !r.halted || !r.halted[e]) return false;
+  if (lane < N) {
+    const size_t idx = ((size_t)r.t * B + e) * N + lane;
+    if (r.rec_reward) r.rec_reward[idx] = 0.f;
+    if (r.rec_mini_mask) r.rec_mini_mask[idx] = 1;
+    if (r.rec_alive) r.rec_alive[idx] = 0;
+  }
+  if (lane == 0) {
+    if (r.rec_episode_mask) r.rec_episode_mask[(size_t)r.t * B + e] = 0;
+    if (r.rec_valid) r.rec_valid[(size_t)r.t * B + e] = 0;
+  }
+  return true;
+}
+
 // Returns true when the episode of env `e` ends at this step
 // (env done, or t == max_steps-1: trainer.py:90, or the batch is cut here).
 __device__ __forceinline__ bool ic3_rollout_tail(const ic3_rollout_io& r, int e, int B, int N, int lane,
@@ -41,10 +60,13 @@ __device__ __forceinline__ bool ic3_rollout_tail(const ic3_rollout_io& r, int e,
   }
   if (lane == 0) {
     if (r.rec_episode_mask) r.rec_episode_mask[(size_t)r.t * B + e] = done_t ? 0 : 1;  // :92-96
+    if (r.rec_valid) r.rec_valid[(size_t)r.t * B + e] = 1;
     r.fresh[e] = done_t ? 1 : 0;
     r.t_ep[e] = done_t ? 0 : tep + 1;
-    if (r.stat_steps) r.stat_steps[e] += 1;                                        // :109
+    int nsteps = 0;
+    if (r.stat_steps) nsteps = (r.stat_steps[e] += 1);                             // :109
     if (done_t) {
+      if (r.batch_size > 0 && r.halted && nsteps >= r.batch_size) r.halted[e] = 1; // trainer.py:231 loop condition
       if (r.stat_episodes) r.stat_episodes[e] += 1;                                // :235
       if (r.stat_success && success > 0) r.stat_success[e] += success;             // :124-125
     }

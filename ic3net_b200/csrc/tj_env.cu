@@ -111,7 +111,9 @@ __global__ void tj_step_kernel(TJArgs a, const int32_t* __restrict__ act, int ac
       rpos = a.st.route_pos[i];
       lact = a.st.last_act[i];
     }
-    if (do_step) {
+    if (do_step && r.has && ic3_rollout_halted(r.io, e, cfg.B, N, lane)) {
+      // this slot has completed its batch (trainer.py:231): nothing moves, null records
+    } else if (do_step) {
       // ---- _take_action :540-581 ----
       int completed = 0;
       const int av = lane < N ? act[i * act_stride] : 1;

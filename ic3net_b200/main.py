@@ -22,7 +22,7 @@ from .action_utils import parse_action_args
 from .comm import CommNetMLP
 from .multi_gpu import MultiGPUTrainer
 from .trainer import Trainer
-from .utils import LogField, init_args_for_env
+from .utils import LogField, init_args_for_env, merge_stat
 
 
 def build_parser():
@@ -103,6 +103,89 @@ def derive_args(args):
     return args
 
 
+LOG_FIELDS = (('epoch', None), ('reward', 'num_episodes'), ('enemy_reward', 'num_episodes'),
+              ('success', 'num_episodes'), ('steps_taken', 'num_episodes'), ('add_rate', 'num_episodes'),
+              ('comm_action', 'num_steps'), ('enemy_comm', 'num_steps'), ('value_loss', 'num_steps'),
+              ('action_loss', 'num_steps'), ('entropy', 'num_steps'))
+
+
+def make_log():
+    """The reference's log table (main.py:194-205): same keys, plot flags, x axes and divisors."""
+    log = dict()
+    for k, d in LOG_FIELDS:
+        log[k] = LogField(list(), k != 'epoch', 'epoch' if k != 'epoch' else None, d)
+    return log
+
+
+def update_log(log, stat):
+    """End-of-epoch bookkeeping with the reference's contract (main.py:218-225), in place on both arguments.
+    The merged ``stat`` of the epoch is normalised field by field -- a field that has a divisor (``num_episodes`` or
+    ``num_steps``) is divided by it when that count is positive -- and EVERY series of the log receives exactly one
+    entry per epoch (0 for a field the epoch did not produce), so all series stay aligned with ``log['epoch']``.
+    Returns the 1-based epoch number."""
+    epoch = len(log['epoch'].data) + 1
+    log['epoch'].data.append(epoch)
+    for name, field in log.items():
+        if name == 'epoch':
+            continue
+        div = field.divide_by
+        if name in stat and div is not None and stat[div] > 0:
+            stat[name] = stat[name] / stat[div]
+        field.data.append(stat.get(name, 0))
+    return epoch
+
+
+# (stat key, line format) in the order the reference prints them (main.py:233-244)
+_EPOCH_LINES = (('enemy_reward', 'Enemy-Reward: {}'), ('add_rate', 'Add-Rate: {:.2f}'), ('success', 'Success: {:.2f}'),
+                ('steps_taken', 'Steps-taken: {:.2f}'), ('comm_action', 'Comm-Action: {}'),
+                ('enemy_comm', 'Enemy-Comm: {}'))
+
+
+def epoch_lines(epoch, stat, epoch_time):
+    """What main.py:227-244 prints for an epoch, as a list of lines (``stat`` already normalised by update_log)."""
+    np.set_printoptions(precision=2)
+    head = 'Epoch {}\tReward {}\tTime {:.2f}s'.format(epoch, stat['reward'], epoch_time)
+    return [head] + [fmt.format(stat[key]) for key, fmt in _EPOCH_LINES if key in stat]
+
+
+class _utils_alias(object):
+    """Checkpoints interchange with the reference (main.py:260-272): its ``log`` is pickled as ``utils.LogField``.
+    Inside this context the name ``utils`` resolves to ic3net_b200.utils and our LogField class pickles under that name, so files written here load in the reference and
+    files written by the reference load here."""
+
+    def __enter__(self):
+        from . import utils as _u
+        self._had = sys.modules.get('utils')
+        sys.modules['utils'] = _u
+        self._mod = LogField.__module__
+        LogField.__module__ = 'utils'
+        return self
+
+    def __exit__(self, *e):
+        LogField.__module__ = self._mod
+        if self._had is None:
+            sys.modules.pop('utils', None)
+        else:
+            sys.modules['utils'] = self._had
+        return False
+
+
+def save_checkpoint(path, policy_net, log, trainer):
+    """main.py:260-265."""
+    d = dict(policy_net=policy_net.state_dict(), log=log, trainer=trainer.state_dict())
+    with _utils_alias():
+        torch.save(d, path)
+
+
+def load_checkpoint(path, policy_net, log, trainer):
+    """main.py:267-272."""
+    with _utils_alias():
+        d = torch.load(path, weights_only=False)
+    policy_net.load_state_dict(d['policy_net'])
+    log.update({k: LogField(*v) for k, v in d['log'].items()})
+    trainer.load_state_dict(d['trainer'])
+
+
 def main(argv=None):
     argv = sys.argv[1:] if argv is None else argv
     parser = build_parser()
@@ -114,12 +197,16 @@ def main(argv=None):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.set_num_threads(1)                         # README.md:48 (OMP_NUM_THREADS=1); host work is tiny
     torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
     if world > 1:
-        torch.distributed.init_process_group("nccl", device_id=torch.device("cuda", local))
-    if args.seed == -1:
-        args.seed = int(np.random.randint(0, 10000))
+        torch.distributed.init_process_group("nccl", device_id=dev)
+    if args.seed == -1:                              # main.py:157-158; ONE draw for the whole job: rank 0's
+        seed = torch.tensor([int(np.random.randint(0, 10000))], dtype=torch.int64, device=dev)
+        if world > 1:
+            torch.distributed.broadcast(seed, src=0)
+        args.seed = int(seed.item())
     args.env_id0 = rank * args.nenvs                 # this rank's slice of the global env ids
-    torch.manual_seed(args.seed)                     # identical initial parameters on every rank
+    torch.manual_seed(args.seed)                     # identical initial parameters on every rank (main.py:159)
 
     env = data.init(args.env_name, args, False)
     num_inputs = env.observation_dim
@@ -140,52 +227,33 @@ def main(argv=None):
 
     args.record_for_grad = not args.rollout_only     # keep the inputs compute_grad re-runs (trainer.py)
     policy_net = CommNetMLP(args, num_inputs)
+    # MultiGPUTrainer broadcasts rank 0's parameters: replicas are identical whatever the ranks' RNG state was
     trainer = MultiGPUTrainer(args, lambda: Trainer(args, policy_net, env))
 
-    log = dict()
-    for k, d in (('epoch', None), ('reward', 'num_episodes'), ('success', 'num_episodes'),
-                 ('steps_taken', 'num_episodes'), ('add_rate', 'num_episodes'), ('comm_action', 'num_steps'),
-                 ('value_loss', 'num_steps'), ('action_loss', 'num_steps'), ('entropy', 'num_steps')):
-        log[k] = LogField(list(), k != 'epoch', 'epoch' if k != 'epoch' else None, d)
-
-    def save(path):
-        d = dict(policy_net=policy_net.state_dict(), log=log, trainer=trainer.state_dict())
-        torch.save(d, path)
-
+    log = make_log()
     if args.load:
-        d = torch.load(args.load, weights_only=False)
-        policy_net.load_state_dict(d['policy_net'])
-        log.update(d['log'])
-        trainer.load_state_dict(d['trainer'])
+        load_checkpoint(args.load, policy_net, log, trainer)
 
-    from .utils import merge_stat
     for ep in range(args.num_epochs):
         epoch_begin = time.time()
         stat = dict()
         for n in range(args.epoch_size):
             if args.rollout_only:
-                batch, s = trainer.trainer.run_batch(ep + 1)
-                s = trainer.reduce(s)
+                batch, s = trainer.run_batch(ep)
             else:
-                s = trainer.train_batch(ep + 1)
+                s = trainer.train_batch(ep)              # main.py:213: the 0-based epoch drives the TJ curriculum
             merge_stat(s, stat)
         epoch_time = time.time() - epoch_begin
-        epoch = len(log['epoch'].data) + 1
-        for k, v in log.items():
-            if k == 'epoch':
-                v.data.append(epoch)
-            elif k in stat and v.divide_by is not None and stat[v.divide_by] > 0:
-                v.data.append(stat[k] / stat[v.divide_by])       # main.py:219-225
+        nsteps = stat.get('num_steps', 0)
+        epoch = update_log(log, stat)
         if rank == 0:
-            print('Epoch {}\tReward {}\tTime {:.2f}s\tsteps/s {:.0f}'.format(
-                epoch, stat['reward'] / max(1, stat['num_episodes']), epoch_time, stat['num_steps'] / epoch_time))
-            for k in ('success', 'steps_taken', 'add_rate', 'comm_action'):
-                if k in stat:
-                    print('{}: {}'.format(k, stat[k] / stat['num_episodes' if k != 'comm_action' else 'num_steps']))
+            for ln in epoch_lines(epoch, stat, epoch_time):
+                print(ln)
+            print('steps/s {:.0f}'.format(nsteps / max(epoch_time, 1e-9)))
         if args.save_every and ep and args.save != '' and ep % args.save_every == 0 and rank == 0:
-            save(args.save + '_' + str(ep))
-    if args.save != '' and rank == 0:
-        save(args.save)
+            save_checkpoint(args.save + '_' + str(ep), policy_net, log, trainer)
+        if args.save != '' and rank == 0:                # main.py:257-258: every epoch
+            save_checkpoint(args.save, policy_net, log, trainer)
     if world > 1:
         torch.distributed.destroy_process_group()
     return 0

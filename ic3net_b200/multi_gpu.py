@@ -8,11 +8,15 @@ RMSprop step (:90-97); ``stat`` dicts are merged with ``merge_stat`` (:86-88).
 Here: one process per GPU (``torch.distributed``; NCCL over NVLink on GPUs, gloo in the CPU
 tests), parameters replicated, environment slots sharded (rank r owns global env ids
 ``[r*B, (r+1)*B)``, i.e. ``args.env_id0 = rank * args.nenvs`` selects its Philox streams).
-Per update exactly ONE gradient collective: an all-reduce(sum) of the flat fp32 gradient
-buffer (parameters without a gradient -- ``hidd_encoder`` -- are skipped like
-multi_processing.py:35,65), then ``grad /= global num_steps`` and the same optimizer step on
-every rank, so the replicas stay bit-identical.  The stat scalars ride a second, ~200-byte
-float64 all-reduce so that step / episode counts stay exact.
+The reference's workers share ONE set of parameters (main.py:177-179 ``share_memory_``); the
+replicas get the same guarantee from a broadcast of rank 0's flat parameter (and optimizer
+state) buffer at construction and after ``load_state_dict``.  Per update exactly ONE gradient
+collective: an all-reduce(sum) of the flat fp32 gradient buffer (parameters without a gradient
+-- ``hidd_encoder`` -- are skipped like multi_processing.py:35,65), then ``grad /= global
+num_steps`` and the same optimizer step on every rank, so the replicas stay bit-identical.  The
+batch statistics and the loss sums never leave the device before they are reduced: they ride a
+second, ~200-byte float64 all-reduce (step / episode counts stay exact) and reach the host in
+ONE copy per update.
 """
 import numbers
 
@@ -82,12 +86,45 @@ class MultiGPUTrainer(object):
         self.rank = dist.get_rank() if _dist_on() else 0
         self.is_random = getattr(args, 'random', False)
         self.collectives = 0          # gradient all-reduces issued (one per update)
+        self.sync_parameters()
 
     def quit(self):
         return
 
+    # ------------------------------------------------------------------ replicas
+    def sync_parameters(self):
+        """Every rank takes rank 0's parameters and optimizer state (the reference's workers share one policy,
+        main.py:177-179).  A no-op for a single process."""
+        if not _dist_on():
+            return
+        opt = self.trainer.optimizer
+        if hasattr(opt, 'flat_params'):
+            dist.broadcast(opt.flat_params, src=0)
+            dist.broadcast(opt.flat_square_avg, src=0)
+            steps = torch.tensor([opt.steps], dtype=torch.int64, device=opt.flat_params.device)
+            dist.broadcast(steps, src=0)
+            opt.steps = int(steps.item())
+            opt.mark_params_changed()
+        else:
+            for p in self.trainer.params:
+                dist.broadcast(p.data, src=0)
+
+    def replica_checksum(self):
+        """(max |param - rank 0's param|) over all ranks; 0.0 when the replicas are bit-identical."""
+        opt = self.trainer.optimizer
+        flat = opt.flat_params if hasattr(opt, 'flat_params') else torch.cat([p.data.reshape(-1) for p in self.trainer.params])
+        if not _dist_on():
+            return 0.0
+        ref = flat.clone()
+        dist.broadcast(ref, src=0)
+        d = (flat - ref).abs().max().reshape(1)
+        dist.all_reduce(d, op=dist.ReduceOp.MAX)
+        return float(d.item())
+
+    # ------------------------------------------------------------------ reductions
     def reduce(self, stat):
-        """Sum gradients and additive stats over ranks; returns the merged stat."""
+        """Sum gradients and additive stats (a HOST dict) over ranks; returns the merged stat.  Generic path
+        (any trainer with ``params`` / ``optimizer``); the device path of train_batch avoids the host dict."""
         params = self.trainer.params
         opt = self.trainer.optimizer
         if hasattr(opt, 'flat_grads'):
@@ -113,16 +150,52 @@ class MultiGPUTrainer(object):
             unflatten_into(flat, grads)
         return stat
 
+    def reduce_device(self, loss_vec=None, with_grads=True):
+        """Device path: all-reduce the flat gradient buffer (in place) and the float64 [batch statistics | loss
+        sums] vector, then ONE device->host copy.  Returns the merged stat dict of all ranks."""
+        tr = self.trainer
+        vec = tr.stat_vector()
+        nstat = vec.numel()
+        if loss_vec is not None:
+            vec = torch.cat([vec, loss_vec.to(vec.dtype)])
+        if _dist_on():
+            if with_grads:
+                dist.all_reduce(tr.optimizer.flat_grads, op=dist.ReduceOp.SUM)     # multi_processing.py:92-94
+                self.collectives += 1
+            dist.all_reduce(vec, op=dist.ReduceOp.SUM)                             # multi_processing.py:86-88
+        host = vec.cpu().numpy()
+        stat = tr.stat_from_vector(host[:nstat])
+        if loss_vec is not None:
+            for i, k in enumerate(tr.LOSS_KEYS):
+                stat[k] = float(host[nstat + i])
+        return stat
+
+    def run_batch(self, epoch):
+        """Rollout only (``--rollout_only``): every rank collects its batch; statistics merged over ranks."""
+        tr = self.trainer
+        T, quota = tr.batch_plan()
+        batch = tr.rollout(T, epoch, quota=quota)
+        return batch, self.reduce_device(None, with_grads=False)
+
     def train_batch(self, epoch):
-        batch, stat = self.trainer.run_batch(epoch)
-        self.trainer.optimizer.zero_grad(set_to_none=False)
-        s = self.trainer.compute_grad(batch)
+        tr = self.trainer
+        if hasattr(tr, 'stat_vector') and hasattr(tr.optimizer, 'flat_grads'):
+            T, quota = tr.batch_plan()
+            batch = tr.rollout(T, epoch, quota=quota)            # no host synchronisation up to reduce_device
+            tr.optimizer.zero_grad(set_to_none=False)
+            loss_vec = tr.compute_grad_device(batch)
+            stat = self.reduce_device(loss_vec)
+            tr.optimizer.step(grad_div=stat['num_steps'])        # multi_processing.py:95-97 in one kernel
+            return stat
+        batch, stat = tr.run_batch(epoch)
+        tr.optimizer.zero_grad(set_to_none=False)
+        s = tr.compute_grad(batch)
         merge_stat(s, stat)
         stat = self.reduce(stat)
-        if hasattr(self.trainer.optimizer, 'flat_grads'):
-            self.trainer.optimizer.step(grad_div=stat['num_steps'])   # multi_processing.py:95-97 in one kernel
+        if hasattr(tr.optimizer, 'flat_grads'):
+            tr.optimizer.step(grad_div=stat['num_steps'])        # multi_processing.py:95-97 in one kernel
         else:
-            self.trainer.optimizer.step()                        # multi_processing.py:97
+            tr.optimizer.step()                                  # multi_processing.py:97
         return stat
 
     def state_dict(self):
@@ -130,3 +203,4 @@ class MultiGPUTrainer(object):
 
     def load_state_dict(self, state):
         self.trainer.load_state_dict(state)
+        self.sync_parameters()

@@ -62,6 +62,7 @@ class FlatRMSprop(object):
 
     def step(self, grad_div=1.0):
         """One update with ``grad / grad_div`` (the trainer passes the global number of env steps)."""
+        self._check_attached()
         for p, g in zip(self.params, self._views(self.flat_grads)):
             if p.grad is None:
                 raise RuntimeError("a parameter lost its flat gradient view; call zero_grad() before backward")
@@ -71,8 +72,12 @@ class FlatRMSprop(object):
         _lib.check(_lib.load().ic3_rmsprop_step(self.numel, self.lr, self.alpha, self.eps, float(grad_div),
                                                 self.flat_grads.data_ptr(), self.flat_params.data_ptr(),
                                                 self.flat_square_avg.data_ptr(), _lib.stream()))
-        # the kernel wrote through raw pointers: bump the version counters so that caches keyed on
-        # (data_ptr, _version) -- CommNetMLP.packed() -- see the new weights
+        self.mark_params_changed()
+        self.steps += 1
+
+    def mark_params_changed(self):
+        """The flat parameter buffer was written through raw pointers / collectives: bump the version counters so
+        that caches keyed on (data_ptr, _version) -- CommNetMLP.packed() -- see the new weights."""
         bump = getattr(torch._C, "_increment_version", None)
         if bump is not None:
             bump(self.params)
@@ -80,7 +85,14 @@ class FlatRMSprop(object):
             with torch.no_grad():
                 for p in self.params:
                     p.add_(0)
-        self.steps += 1
+
+    def _check_attached(self):
+        """A second FlatRMSprop built on the same parameters re-points them to ITS buffers (the reference builds
+        several Trainers on one policy_net, main.py:181-186): updating an orphaned buffer would be a silent no-op."""
+        for p, v in zip(self.params, self._views(self.flat_params)):
+            if p.data_ptr() != v.data_ptr():
+                raise RuntimeError("a parameter no longer lives in this optimizer's flat buffer (another FlatRMSprop "
+                                   "was built on the same policy_net); use ONE optimizer per policy_net")
 
     def state_dict(self):
         state = {}

@@ -3,10 +3,13 @@
 
 ``Trainer(args, policy_net, env)`` drives ``env.nenvs`` independent environment slots in
 lock-step on one GPU.  Each slot plays the role of one reference process: it runs episode after
-episode (auto-reset, hidden state zeroed, nobody talks at t = 0), and ``run_batch`` returns once
-every slot has produced ``>= batch_size`` steps (``ceil(batch_size / max_steps) * max_steps``
-lock-step iterations; an episode still open at the end of the batch is cut there, which is the
-only deviation from trainer.py:231-237, where the last episode may overshoot instead).
+episode (auto-reset, hidden state zeroed, nobody talks at t = 0), and ``run_batch`` follows the
+reference's batch boundary (trainer.py:231-237): a slot plays WHOLE episodes until it holds
+``>= batch_size`` steps -- its last episode overshoots -- and then halts (the lock-step loop runs
+``batch_size + max_steps - 1`` iterations when episodes can end early, ``ceil(batch_size /
+max_steps) * max_steps`` when they cannot; halted slots leave null records with ``valid = 0``).
+``args.batch_boundary = 'cut'`` selects the round-1 behaviour instead (a fixed number of lock-steps,
+episodes still open at the end are cut there).
 
 Rollout (the hot path): one lock-step iteration is a handful of kernel launches and no host
 synchronisation:
@@ -37,7 +40,7 @@ Transition = namedtuple('Transition', ('state', 'action', 'action_out', 'value',
                                        'episode_mini_mask', 'next_state', 'reward', 'misc'))
 
 RolloutBatch = namedtuple('RolloutBatch', ('action', 'logp', 'value', 'reward', 'episode_mask',
-                                           'episode_mini_mask', 'alive_mask', 'snapshot'))
+                                           'episode_mini_mask', 'alive_mask', 'valid'))
 
 
 class Trainer(object):
@@ -57,6 +60,7 @@ class Trainer(object):
         self.grad_window = int(getattr(args, 'grad_window', 40))
         self._buf = None
         self._graph = None
+        self._graph_key = None
         # encoder layout of this environment (class terms / counts summed separately, comm.py set_obs_layout) and
         # the per-position table of the class terms for the fused index encoder, rebuilt when the weights change
         policy_net.set_obs_layout(*getattr(env.env, 'obs_layout', (0, 0, 0)))
@@ -94,7 +98,8 @@ class Trainer(object):
                  ralive=z(T, B, N, dtype=torch.uint8), step_reward=z(B, N),
                  stat_reward=z(B, N), stat_comm=z(B, N), stat_success=z(B, dtype=torch.int32),
                  stat_episodes=z(B, dtype=torch.int32), stat_steps=z(B, dtype=torch.int32),
-                 err=z(1, dtype=torch.int32))
+                 err=z(1, dtype=torch.int32), halted=z(B, dtype=torch.uint8), valid=z(T, B, dtype=torch.uint8),
+                 statvec=z(4 + 2 * N, dtype=torch.float64))
         if self.obs_mode == 'dense' or (self.record_for_grad and self.is_tj):
             b['obs'] = torch.empty(B, N, self.env.observation_dim, dtype=torch.float32, device=dev)
         if self.record_for_grad:
@@ -144,8 +149,10 @@ class Trainer(object):
         W = 2 * self.env.env.vision + 1
         return (not dense) and self.policy_net.policy_impl == 'tc' and W * W <= 25
 
-    def _enqueue(self, T):
-        """Enqueue T lock-step iterations on the current stream (no host sync)."""
+    def _enqueue(self, T, quota=0):
+        """Enqueue T lock-step iterations on the current stream (no host sync).  quota > 0: reference batch
+        boundary -- a slot halts at the first episode end with >= quota steps (ic3_rollout_io.batch_size);
+        quota = 0: episodes still open at iteration T-1 are cut there."""
         b, e, net, args = self._buf, self.env.env, self.policy_net, self.args
         lib = _lib.load()
         B, N = e.nenvs, args.nagents
@@ -202,7 +209,9 @@ class Trainer(object):
                                workspace=_lib.ptr(ws), err=b['err'].data_ptr(), **src)
             _lib.check(lib.ic3_policy_step(C.byref(cfg), C.byref(w), C.byref(io), s))
             r = _lib.RolloutIO(t=t, max_steps=args.max_steps, nheads=nh, hard_attn=hard,
-                               comm_action_one=int(bool(args.comm_action_one)), last=int(t == T - 1),
+                               comm_action_one=int(bool(args.comm_action_one)),
+                               last=int(t == T - 1 and quota <= 0), batch_size=int(quota),
+                               halted=b['halted'].data_ptr(), rec_valid=b['valid'].data_ptr(),
                                action=b['action'][t].data_ptr(), t_ep=b['t_ep'].data_ptr(),
                                fresh=b['fresh'].data_ptr(), comm_next=b['comm'].data_ptr(),
                                alive_next=b['alive'].data_ptr(), rec_reward=b['reward'].data_ptr(),
@@ -223,13 +232,13 @@ class Trainer(object):
             e.reset(epoch, want_obs=False)
         else:
             e.reset(want_obs=False)
-        for k in ('stat_reward', 'stat_comm', 'stat_success', 'stat_episodes', 'stat_steps', 't_ep'):
+        for k in ('stat_reward', 'stat_comm', 'stat_success', 'stat_episodes', 'stat_steps', 't_ep', 'halted'):
             b[k].zero_()
         b['fresh'].fill_(1)
 
-    def rollout(self, T, epoch=0):
-        """T lock-step iterations from fresh episodes in every slot.  Returns a RolloutBatch of
-        stacked [T, B, ...] device tensors (views of the trainer's record buffers)."""
+    def rollout(self, T, epoch=0, quota=0):
+        """T lock-step iterations from fresh episodes in every slot (``quota``: see _enqueue).  Returns a
+        RolloutBatch of stacked [T, B, ...] device tensors (views of the trainer's record buffers)."""
         e = self.env.env
         if self._buf is None or self._buf['T'] != T:
             self._alloc(T)
@@ -240,54 +249,91 @@ class Trainer(object):
         if self._fused_x():
             self._encoder_table(self.policy_net.policy_cfg(e.nenvs), w)  # ... and the encoder table with them
         if self.use_graph:
-            if self._graph is None:
-                self._enqueue(T)                  # warm-up (lazy function attributes, allocator)
+            # kernel arguments passed BY VALUE are frozen into a captured graph: everything of that kind that can
+            # change between rollouts is part of the key (the TJ curriculum moves cfg.spawn_thr, traffic_junction_env.py:
+            # 196-200,620-626; a re-seeded env changes cfg.seed) and a stale graph is re-captured
+            key = (T, int(quota), int(getattr(e.cfg, 'spawn_thr', 0)), int(e.cfg.seed), int(e.cfg.env_id0))
+            if self._graph is None or self._graph_key != key:
+                self._enqueue(T, quota)           # warm-up (lazy function attributes, allocator)
                 torch.cuda.synchronize()
                 self._episode_boundary(epoch)
                 g = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(g):
-                    self._enqueue(T)
-                self._graph = g
+                    self._enqueue(T, quota)
+                self._graph, self._graph_key = g, key
                 g.replay()
             else:
                 self._graph.replay()
         else:
-            self._enqueue(T)
+            self._enqueue(T, quota)
         return RolloutBatch(action=b['action'], logp=b['logp'], value=b['value'].view(T, e.nenvs, -1),
                             reward=b['reward'], episode_mask=b['emask'], episode_mini_mask=b['mini'],
-                            alive_mask=b['ralive'], snapshot=None)
+                            alive_mask=b['ralive'], valid=b['valid'])
 
-    def collect_stat(self):
-        """Host-side stat dict with the reference's keys (trainer.py:73-75,86-88,109-110,124-125),
-        summed over the env slots of this GPU."""
-        b, e, args = self._buf, self.env.env, self.args
-        flags = int(b['err'].item())
+    def stat_vector(self):
+        """Device float64 vector [num_episodes, num_steps, success, err flags, reward[N], comm_action[N]] of this
+        GPU's slots (one kernel, csrc/returns.cu ic3_stat_reduce); no host synchronisation."""
+        b, e = self._buf, self.env.env
+        hard = bool(self.args.hard_attn) and bool(self.args.commnet)
+        _lib.check(_lib.load().ic3_stat_reduce(e.nenvs, self.args.nagents, b['stat_episodes'].data_ptr(),
+                                               b['stat_steps'].data_ptr(), b['stat_success'].data_ptr(),
+                                               b['err'].data_ptr(), b['stat_reward'].data_ptr(),
+                                               b['stat_comm'].data_ptr() if hard else None,
+                                               b['statvec'].data_ptr(), _lib.stream()))
+        return b['statvec']
+
+    def stat_from_vector(self, v):
+        """Host-side stat dict with the reference's keys (trainer.py:73-75,86-88,109-110,124-125,235) from a
+        stat_vector() (of this GPU, or summed over ranks) that has been copied to the host."""
+        args, N = self.args, self.args.nagents
+        flags = int(v[3])
         if flags:
             raise RuntimeError("device-side error flag %#x during rollout" % flags)
         stat = dict()
-        stat['num_episodes'] = int(b['stat_episodes'].sum().item())
-        stat['num_steps'] = int(b['stat_steps'].sum().item())
+        stat['num_episodes'] = int(round(float(v[0])))
+        stat['num_steps'] = int(round(float(v[1])))
         stat['steps_taken'] = stat['num_steps']
-        stat['reward'] = b['stat_reward'].sum(0).double().cpu().numpy()
+        stat['reward'] = v[4:4 + N].copy()
         if args.hard_attn and args.commnet:
-            stat['comm_action'] = b['stat_comm'].sum(0).double().cpu().numpy()
+            stat['comm_action'] = v[4 + N:4 + 2 * N].copy()
         if not (not self.is_tj and args.mode == 'competitive'):
-            stat['success'] = int(b['stat_success'].sum().item())
+            stat['success'] = int(round(float(v[2])))
         if self.is_tj:
-            stat['add_rate'] = e.add_rate * stat['num_episodes']
+            # every episode of the batch reports the same env.stat['add_rate'] (traffic_junction_env.py:249-250),
+            # merged by + over episodes and workers (trainer.py:124-125, utils.py:15-29)
+            stat['add_rate'] = self.env.env.add_rate * stat['num_episodes']
         return stat
+
+    def collect_stat(self):
+        """Stat dict of the last rollout, summed over the env slots of this GPU (ONE device->host copy)."""
+        return self.stat_from_vector(self.stat_vector().cpu().numpy())
 
     # ------------------------------------------------------------------ reference surface
     def get_episode(self, epoch):
-        """One episode horizon (max_steps lock-step iterations) for every env slot."""
-        batch = self.rollout(self.args.max_steps, epoch)
+        """Exactly one episode per env slot (trainer.py:26-126): max_steps lock-step iterations, a slot whose
+        episode ends early halts (``valid`` = 0 afterwards)."""
+        batch = self.rollout(self.args.max_steps, epoch, quota=1)
         return batch, self.collect_stat()
 
+    def episodes_end_early(self):
+        """Can an episode end before max_steps?  predator_prey 'mixed' mode only (predator_prey_env.py:273-274);
+        traffic_junction never sets episode_over (traffic_junction_env.py:219,252)."""
+        return (not self.is_tj) and getattr(self.args, 'mode', 'mixed') == 'mixed'
+
+    def batch_plan(self):
+        """(lock-step iterations, quota) of one run_batch."""
+        bs, ms = int(self.args.batch_size), int(self.args.max_steps)
+        full = int(math.ceil(bs / float(ms))) * ms
+        if getattr(self.args, 'batch_boundary', 'reference') == 'cut':
+            return full, 0
+        return (bs + ms - 1 if self.episodes_end_early() else full), bs
+
     def steps_per_batch(self):
-        return int(math.ceil(self.args.batch_size / float(self.args.max_steps))) * self.args.max_steps
+        return self.batch_plan()[0]
 
     def run_batch(self, epoch):
-        batch = self.rollout(self.steps_per_batch(), epoch)
+        T, quota = self.batch_plan()
+        batch = self.rollout(T, epoch, quota=quota)
         self.stats = self.collect_stat()
         return batch, self.stats
 
@@ -354,10 +400,11 @@ class Trainer(object):
             act = b['action'][t].long()
             lp_taken = torch.zeros(B, N, device=h.device)
             ent = torch.zeros((), device=h.device)
+            vmask = b['valid'][t].float().view(B, 1, 1)            # 0 for slots that already completed their batch
             for k, head in enumerate(net.heads):
                 lp = F.log_softmax(head(h), dim=-1).view(B, N, -1)                         # comm.py:239
                 lp_taken = lp_taken + lp.gather(-1, act[..., k:k + 1]).squeeze(-1)         # utils.py:42-46
-                ent = ent - (lp * lp.exp()).sum()
+                ent = ent - (lp * lp.exp() * vmask).sum()
             a_loss = (-adv[t] * lp_taken * alive_post).sum()                               # trainer.py:198-201
             v_loss = ((value - ret[t]).pow(2) * alive_post).sum()                          # :205-208
             step_loss = a_loss + args.value_coeff * v_loss
@@ -371,10 +418,19 @@ class Trainer(object):
                 c = torch.where(det, c.detach(), c)
         return loss, h, c, st
 
+    LOSS_KEYS = ('action_loss', 'value_loss', 'entropy')
+
     def compute_grad(self, batch):
         """REINFORCE + value + entropy loss summed over every slot and step of the batch, gradients
         accumulated into ``p.grad`` (not yet divided by num_steps: train_batch does that,
-        trainer.py:251-253).  Needs ``args.record_for_grad`` during the rollout."""
+        trainer.py:251-253).  Needs ``args.record_for_grad`` during the rollout.  Returns the reference's stat
+        dict (trainer.py:222-225)."""
+        v = self.compute_grad_device(batch).cpu().numpy()
+        return {k: float(v[i]) for i, k in enumerate(self.LOSS_KEYS)}
+
+    def compute_grad_device(self, batch):
+        """compute_grad without a host synchronisation: the three loss sums come back as a float64 DEVICE vector
+        (LOSS_KEYS order) so the data-parallel trainer can reduce them together with the batch statistics."""
         if not self.record_for_grad:
             raise RuntimeError("set args.record_for_grad = True before the rollout to use compute_grad")
         b, args = self._buf, self.args
@@ -385,14 +441,19 @@ class Trainer(object):
                                                 b['reward'].data_ptr(), b['emask'].data_ptr(), b['mini'].data_ptr(),
                                                 ret.data_ptr(), _lib.stream()))
         adv = ret - b['value'].view(T, B, N)                                               # trainer.py:176-177
-        if args.normalize_rewards:                                                         # :179-180, per slot
-            adv = (adv - adv.mean((0, 2), keepdim=True)) / adv.std((0, 2), keepdim=True)
+        if args.normalize_rewards:                                   # :179-180, per slot, over its REAL steps only
+            v = b['valid'].float().unsqueeze(-1)                     # [T, B, 1]
+            cnt = v.sum(0, keepdim=True) * N
+            mean = (adv * v).sum((0, 2), keepdim=True) / cnt
+            var = (((adv - mean) * v) ** 2).sum((0, 2), keepdim=True) / (cnt - 1)      # torch.std: unbiased
+            adv = (adv - mean) / var.sqrt()
         W = self.grad_window
         nw = (T + W - 1) // W
         dh = dc = None
-        tot = dict(action_loss=0.0, value_loss=0.0, entropy=0.0)
         if getattr(args, 'grad_impl', 'autograd') == 'manual':
-            return self._compute_grad_manual(adv, ret, W, nw)
+            tot = self._compute_grad_manual(adv, ret, W, nw)
+            return torch.tensor([tot[k] for k in self.LOSS_KEYS], dtype=torch.float64, device=e.device)
+        tot = torch.zeros(3, dtype=torch.float64, device=e.device)
         for k in reversed(range(nw)):
             t0, t1 = k * W, min(T, (k + 1) * W)
             h0 = b['ck_h'][k].clone().requires_grad_(True)
@@ -402,8 +463,7 @@ class Trainer(object):
                 loss = loss + (h1 * dh).sum() + (c1 * dc).sum()
             loss.backward()
             dh, dc = h0.grad.detach(), c0.grad.detach()
-            for key in tot:
-                tot[key] += float(st[key].item())
+            tot += torch.stack([st[key] for key in self.LOSS_KEYS]).double()
         return tot
 
     def _compute_grad_manual(self, adv, ret, W, nw):
@@ -427,7 +487,7 @@ class Trainer(object):
         else:
             obs_fn = lambda t: self._pp_sparse_obs(b['s_loc'][t])
         rec = dict(fresh=b['s_fresh'], comm=b['s_comm'], alive=b['s_alive'], t_ep=b['s_tep'], action=b['action'],
-                   alive_post=b['ralive'], obs=obs_fn)
+                   alive_post=b['ralive'], obs=obs_fn, valid=b['valid'])
         tot = dict(action_loss=0.0, value_loss=0.0, entropy=0.0)
         dh = dc = None
         for k in reversed(range(nw)):

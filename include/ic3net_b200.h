@@ -107,6 +107,14 @@ typedef struct {
   int32_t* stat_success;   /* [B] += env.stat['success'] at episode end (trainer.py:124-125) */
   int32_t* stat_episodes;  /* [B] += 1 at episode end   (trainer.py:235) */
   int32_t* stat_steps;     /* [B] += 1 every step       (trainer.py:109) */
+  /* Reference batch boundary (trainer.py:227-237: whole episodes until the worker holds >= batch_size steps, the
+   * last episode overshoots).  batch_size > 0 with halted != NULL: a slot halts at the first episode end at which
+   * stat_steps[slot] >= batch_size and is skipped by every later lock-step (null records).  With
+   * T >= batch_size + max_steps - 1 lock-steps every slot halts by itself and `last` stays 0.  0 / NULL: off. */
+  int32_t batch_size;
+  int32_t reserved0;
+  uint8_t* halted;         /* [B] in/out: slot has completed its batch */
+  uint8_t* rec_valid;      /* [T, B] 1 = a real step of this slot, 0 = slot already halted (may be NULL) */
 } ic3_rollout_io;
 
 /* reset(): predator_prey_env.py:146-168.  Draws N+1 distinct cells per env from
@@ -285,6 +293,11 @@ uint64_t ic3_policy_workspace_bytes(const ic3_policy_cfg* cfg);
 /* One CommNetMLP.forward (recurrent branch, comm_passes = 1) + select_action. */
 int ic3_policy_step(const ic3_policy_cfg* cfg, const ic3_policy_packed* w, const ic3_policy_io* io,
                     void* stream);
+/* Measurement aid (bench.py "roofline_tensor"): ic3_policy_step on the tcgen05 path with CUDA events between its
+ * kernels; synchronises the stream and returns ms[3] = device time of {operand preparation (+ fused encoder),
+ * LSTM/comm tensor-core kernel, heads + sampling}.  Not for the production loop. */
+int ic3_policy_step_profile(const ic3_policy_cfg* cfg, const ic3_policy_packed* w, const ic3_policy_io* io,
+                            void* stream, float* ms);
 /* select_action alone (action_utils.py:32-36) on given log-probabilities. */
 int ic3_sample_actions(const ic3_policy_cfg* cfg, const float* logp, const uint32_t* tick,
                        const uint32_t* draws, int32_t* action, void* stream);
@@ -295,6 +308,15 @@ int ic3_sample_actions(const ic3_policy_cfg* cfg, const float* logp, const uint3
 /* reward, mini_mask: [T,B,N]; episode_mask: [T,B]; returns out: [T,B,N] float32 (float64 accumulation). */
 int ic3_returns_scan(int32_t T, int32_t B, int32_t N, float gamma, float mean_ratio, const float* reward,
                      const uint8_t* episode_mask, const uint8_t* mini_mask, float* returns, void* stream);
+
+/* Batch statistics of Trainer.run_batch (trainer.py:73-75,86-88,109-110,124-125,235; merged over workers by
+ * multi_processing.py:86-88): the per-slot accumulators of ic3_rollout_io summed over the B env slots of this GPU
+ * into one float64 device vector  out[4 + 2N] = [num_episodes, num_steps, success, err flag word, reward[N],
+ * comm_action[N]]  (stat_comm may be NULL: zeros).  One device->host copy per update instead of one per key; the
+ * data-parallel trainer all-reduces the vector before reading it. */
+int ic3_stat_reduce(int32_t B, int32_t N, const int32_t* stat_episodes, const int32_t* stat_steps,
+                    const int32_t* stat_success, const int32_t* err, const float* stat_reward,
+                    const float* stat_comm, double* out, void* stream);
 
 /* ------------------------------------------------------------------------
  * Optimizer step  (trainer.py:21-22 RMSprop(lr, alpha=0.97, eps=1e-6); trainer.py:251-256 and

@@ -574,7 +574,42 @@ def gen_rmsprop_case(name, seed, nupdates=5, lr=0.001):
     save(name, meta, **arrays)
 
 
+def gen_log_case(name="log_contract"):
+    """Per-epoch log / print contract: outputs of the reference's own main.py statements (oracle/ref_log.py) for a
+    fixed sequence of epoch stats -> tests/golden/log_contract.json."""
+    import copy
+    import json
+    from . import ref_log
+    rs = np.random.RandomState(11)
+
+    def epoch(kind, n=4):
+        ne, ns = int(rs.randint(1, 200)), int(rs.randint(50, 9000))
+        st = dict(num_episodes=ne, num_steps=ns, reward=(rs.randn(n) * ne).tolist(), steps_taken=ns,
+                  value_loss=float(rs.rand() * ns), action_loss=float(rs.randn() * ns), entropy=float(rs.rand() * ns))
+        if kind in ("pp", "tj"):
+            st["success"] = int(rs.randint(0, ne + 1))
+            st["comm_action"] = rs.randint(0, ns, size=n).astype(np.float64).tolist()
+        if kind == "tj":
+            st["add_rate"] = 0.05 * ne
+        if kind == "empty":
+            st["num_episodes"] = 0
+        return st
+    epochs = [epoch(k) for k in ("pp", "tj", "plain", "empty", "tj", "pp")]
+    log = ref_log.make_log()
+    lines = []
+    for st in epochs:
+        st = {k: (np.asarray(v) if isinstance(v, list) else v) for k, v in copy.deepcopy(st).items()}
+        lines.append(ref_log.epoch_update(log, st, 1.2345))
+    conv = lambda x: x.tolist() if isinstance(x, np.ndarray) else (x.item() if isinstance(x, np.generic) else x)
+    out = dict(epochs=epochs, lines=lines, log={k: [conv(x) for x in f.data] for k, f in log.items()})
+    with open(os.path.join(GOLDEN, name + ".json"), "w") as f:
+        json.dump(out, f, indent=0)
+
+
 def main():
+    if "--log-only" in sys.argv:
+        gen_log_case()
+        return 0
     if "--rmsprop-only" in sys.argv:          # needs torch only, not the reference checkout
         gen_rmsprop_case("rmsprop_ref", 81)
         return 0
@@ -639,6 +674,7 @@ def main():
                   max_steps=20, hid_size=64, commnet=True, difficulty="easy", add_rate_min=0.3, add_rate_max=0.3,
                   batch_size=50, mean_ratio=0.5, gamma=0.9)
     gen_rmsprop_case("rmsprop_ref", 81)
+    gen_log_case()
     return 0
 
 

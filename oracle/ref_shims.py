@@ -1,8 +1,9 @@
 """Import the UNMODIFIED reference from /root/reference (this container only).
 
 TEST INFRASTRUCTURE.  Used by ``oracle/gen_golden.py`` (fixture generation) and
-by ``tests/test_oracle_vs_reference.py`` (skipped when /root/reference is
-absent, e.g. on the GPU box).  Nothing here changes reference arithmetic; the
+by ``oracle/ref_baseline.py`` (the CPU baseline of record: the reference's own
+``MultiProcessTrainer`` timed on the host cores; on the GPU box it runs from the
+staged copy ``oracle/_ref``, see ``oracle/build_ref.py``).  Nothing here changes reference arithmetic; the
 shims only make 2018-era code importable on python 3.12 / numpy 2.3 / torch 2.11
 (SURVEY.md section 8(c)):
 
@@ -28,7 +29,18 @@ import types
 
 import numpy as np
 
-REF_ROOT = os.environ.get("IC3NET_REFERENCE", "/root/reference")
+def _find_ref_root():
+    """/root/reference in the development container; the staged copy ``oracle/_ref`` (oracle/build_ref.py,
+    git-ignored, shipped by gpurun) on the GPU box."""
+    cands = [os.environ.get("IC3NET_REFERENCE"), "/root/reference",
+             os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")]
+    for c in cands:
+        if c and os.path.isdir(os.path.join(c, "ic3net-envs", "ic3net_envs")):
+            return c
+    return "/root/reference"
+
+
+REF_ROOT = _find_ref_root()
 
 
 def reference_available():

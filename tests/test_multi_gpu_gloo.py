@@ -186,3 +186,48 @@ def test_two_rank_reduction_flat_gradient_buffer():
             assert np.allclose(a, b.numpy(), rtol=1e-6, atol=1e-7)
     for a, b in zip(res[0][2], res[1][2]):
         assert np.array_equal(a, b)
+
+
+class SkewedTrainer(FakeTrainer):
+    """Every rank builds its policy from a DIFFERENT seed (what an unseeded `--seed -1` launch used to do)."""
+
+    def __init__(self, rank):
+        super().__init__(rank)
+        torch.manual_seed(1000 + rank)
+        with torch.no_grad():
+            for p in self.params:
+                p.copy_(torch.randn_like(p))
+
+
+def _skew_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from ic3net_b200.multi_gpu import MultiGPUTrainer
+    import argparse
+    tr = SkewedTrainer(rank)
+    before = [p.detach().numpy().copy() for p in tr.params]
+    mt = MultiGPUTrainer(argparse.Namespace(random=False), lambda: tr)
+    after = [p.detach().numpy().copy() for p in mt.trainer.params]
+    diff0 = mt.replica_checksum()
+    mt.train_batch(0)
+    q.put((rank, before, after, diff0, mt.replica_checksum()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_replicas_take_rank0_parameters_at_construction():
+    """The reference's workers share ONE policy (main.py:177-179); ranks that start from different parameters must
+    be made identical by MultiGPUTrainer itself (broadcast from rank 0) and stay identical after an update."""
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    ps = [ctx.Process(target=_skew_worker, args=(r, world, port, q)) for r in range(world)]
+    [p.start() for p in ps]
+    res = sorted([q.get(timeout=120) for _ in ps], key=lambda x: x[0])
+    [p.join(timeout=60) for p in ps]
+    (_, b0, a0, d0, e0), (_, b1, a1, d1, e1) = res
+    assert any(not np.array_equal(x, y) for x, y in zip(b0, b1))       # they really started apart
+    for x, y, z in zip(a0, a1, b0):
+        assert np.array_equal(x, y) and np.array_equal(x, z)          # both now hold rank 0's values
+    assert d0 == d1 == 0.0 and e0 == e1 == 0.0
