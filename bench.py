@@ -371,12 +371,15 @@ def gpu_arm(opts):
     # ---- full training update: MultiGPUTrainer.train_batch on every rank (rollout with the reference batch boundary
     #      + compute_grad + gradient / statistics all-reduce + RMSprop), SURVEY 8(f)-1/2 + 8(e) ----
     train = None
-    if not opts.quick and opts.train_updates > 0:
+    skip = set(x for x in opts.skip.split(",") if x)
+    if opts.quick:
+        skip |= {"train", "e2e", "index", "cpu"}
+    if "train" not in skip and opts.train_updates > 0:
         train = train_leg(opts, build, MultiGPUTrainer, world, dev, dist, torch)
 
     # ---- e2e: the public, reference-shaped API with host-side actions / rewards, on EVERY rank ----
     e2e = None
-    if not opts.quick:
+    if "e2e" not in skip:
         if world > 1:
             dist.barrier()
         mine = e2e_loop(a, env, net, min(max(K, 50), 200), np, torch, select_action)
@@ -406,7 +409,7 @@ def gpu_arm(opts):
         peak_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
 
         # ---- per-kernel device times (separate pass, CUDA events around every launch) ----
-        kern = per_kernel_times(tr, a, env, net, min(K, 20), C, torch, _lib)
+        kern = per_kernel_times(tr, a, env, net, min(K, 20), C, torch, _lib) if "kernels" not in skip else {}
         is_pp = a.env_name == "predator_prey"
         state_bytes = 32 if is_pp else 64
         obs_bytes = (4 * O + state_bytes) * B * N             # obs written once + state/action/reward
@@ -451,7 +454,7 @@ def gpu_arm(opts):
 
         # ---- fused index-form rollout (no [B,N,O] tensor): the mode the trainer uses by default ----
         alt = None
-        if opts.obs_mode == "dense" and world == 1 and not opts.quick:
+        if opts.obs_mode == "dense" and world == 1 and "index" not in skip:
             a2, env2, net2, tr2 = build("index")
             run2 = Runner(tr2)
             run2.warm(W)
@@ -465,7 +468,7 @@ def gpu_arm(opts):
         # ---- CPU baseline (bounded sample of the same workload on the host cores) ----
         cores = host_cores()
         cpu = None
-        if world == 1 and not opts.quick:
+        if world == 1 and "cpu" not in skip:
             try:
                 r = run_reference(opts.workload, ["rollout"], 1, 4)
                 v, secs = ref_rate(r["modes"]["rollout"]["samples"][1:], N)
@@ -736,7 +739,8 @@ def main():
     ap.add_argument("--train_batch_size", type=int, default=500, help="--batch_size of the train_batch leg (reference default)")
     ap.add_argument("--grad_impl", default="autograd", choices=["autograd", "manual", "kernels"])
     ap.add_argument("--grad_window", type=int, default=40)
-    ap.add_argument("--quick", action="store_true", help="skip the e2e / index / CPU legs (profiling runs)")
+    ap.add_argument("--quick", action="store_true", help="skip the e2e / index / CPU / train legs (profiling runs)")
+    ap.add_argument("--skip", default="", help="comma list of legs to skip: train,e2e,kernels,index,cpu")
     ap.add_argument("--obs_chunk_mb", type=float, default=0.0,
                     help="dense rollout: gather + encode observations in chunks of env slots of at most this size "
                          "(experiment; 0 = the whole batch at once, the measured optimum)")

@@ -115,7 +115,7 @@ def test_train_batch_updates_parameters():
     for n, c in zip(names, changed):
         assert c == (not n.startswith("hidd_encoder")), n      # the unused module gets no gradient (comm.py:57)
     stat2 = tr.train_batch(1)                                  # re-packed weights, second update runs
-    assert stat2["num_steps"] == stat["num_steps"]
+    assert 64 * args.batch_size <= stat2["num_steps"] <= 64 * tr.steps_per_batch()
 
 
 @pytest.mark.parametrize("name", golden_names("grad_"))
