@@ -20,6 +20,8 @@ LSTM_IMG_BYTES = 1572864
 ERR_EPISODE_DONE = 1
 ERR_ROUTE_OVERRUN = 2
 ERR_BAD_ACTION = 4
+ERR_PIPELINE = 0x100
+ERR_FP16_RANGE = 0x200
 
 PP_MODES = {"mixed": 0, "cooperative": 1, "competitive": 2}
 
@@ -71,7 +73,7 @@ class PolicyParams(C.Structure):
 
 class PolicyPacked(C.Structure):
     _fields_ = [("enc_wT", _p), ("enc_b", _p), ("c_wT", _p), ("c_b", _p), ("lstm_wT", _p), ("lstm_b", _p),
-                ("head_w", _p), ("head_b", _p), ("lstm_img", _p), ("bias_cat", _p)]
+                ("head_w", _p), ("head_b", _p), ("lstm_img", _p), ("bias_cat", _p), ("flags", _p)]
 
 
 class PolicyIO(C.Structure):
@@ -79,6 +81,19 @@ class PolicyIO(C.Structure):
                 ("draws", _p), ("h_out", _p), ("c_out", _p), ("value", _p), ("logp", _p), ("action", _p),
                 ("workspace", _p), ("err", _p), ("pp_env", _p), ("pp_state", _p), ("tj_env", _p), ("tj_state", _p),
                 ("x_table", _p)]
+
+
+class BpttPlan(C.Structure):
+    _fields_ = [("cfg", C.POINTER(PolicyCfg)), ("w", C.POINTER(PolicyPacked)), ("pp_env", C.POINTER(PPCfg)),
+                ("tj_env", C.POINTER(TJCfg)), ("x_table", _p), ("value_coeff", C.c_float), ("entr", C.c_float),
+                ("workspace", _p)]
+
+
+class BpttStepIO(C.Structure):
+    _fields_ = [("h_prev", _p), ("c_prev", _p), ("h_new", _p), ("fresh", _p), ("comm", _p), ("alive", _p), ("cut", _p),
+                ("pp_loc", _p), ("tj_loc", _p), ("tj_alive", _p), ("tj_last_act", _p), ("tj_route_id", _p),
+                ("logp", _p), ("action", _p), ("value", _p), ("ret", _p), ("adv", _p), ("alive_post", _p),
+                ("valid", _p), ("dh", _p), ("dc", _p), ("err", _p)]
 
 
 # every symbol include/ic3net_b200.h declares: name -> (restype, argtypes)
@@ -110,6 +125,10 @@ SYMBOLS = {
     "ic3_sample_actions": (C.c_int, [C.POINTER(PolicyCfg), _PTR, _PTR, _PTR, _PTR, _PTR]),
     "ic3_returns_scan": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_float, C.c_float, _PTR, _PTR, _PTR, _PTR,
                                    _PTR]),
+    "ic3_bptt_workspace_bytes": (C.c_uint64, [C.POINTER(BpttPlan)]),
+    "ic3_bptt_begin": (C.c_int, [C.POINTER(BpttPlan), C.c_float, _PTR]),
+    "ic3_bptt_step": (C.c_int, [C.POINTER(BpttPlan), C.POINTER(BpttStepIO), _PTR]),
+    "ic3_bptt_finish": (C.c_int, [C.POINTER(BpttPlan), C.POINTER(PolicyParams), C.POINTER(PolicyParams), _PTR, _PTR]),
     "ic3_stat_reduce": (C.c_int, [C.c_int32, C.c_int32, _PTR, _PTR, _PTR, _PTR, _PTR, _PTR, _PTR, _PTR]),
     "ic3_rmsprop_step": (C.c_int, [C.c_int64, C.c_float, C.c_float, C.c_float, C.c_float, _PTR, _PTR, _PTR, _PTR]),
 }

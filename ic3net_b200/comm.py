@@ -130,6 +130,7 @@ class CommNetMLP(nn.Module):
             if self.policy_impl == 'tc':
                 self._bufs['lstm_img'] = torch.empty(_lib.LSTM_IMG_BYTES, dtype=torch.uint8, device=dev)
                 self._bufs['bias_cat'] = torch.empty(4 * H, device=dev)
+                self._bufs['flags'] = torch.zeros(1, dtype=torch.int32, device=dev)
             self._packed = _lib.PolicyPacked(**{k: v.data_ptr() for k, v in self._bufs.items()})
         for p in ps:
             assert p.is_cuda and p.dtype == torch.float32 and p.is_contiguous()

@@ -58,6 +58,12 @@ class Trainer(object):
         self.is_tj = args.env_name == 'traffic_junction'
         self.record_for_grad = bool(getattr(args, 'record_for_grad', False))
         self.grad_window = int(getattr(args, 'grad_window', 40))
+        # compute_grad implementation: 'kernels' = hand-written BPTT (csrc/bptt_tc.cu; tensor-core policy path, at most
+        # 7 action logits, observation pattern of <= 512 columns), 'autograd' = windowed recompute under torch autograd,
+        # 'manual' = explicit formulas with torch GEMMs (bptt.py).  Default: kernels when the configuration allows.
+        self.grad_impl = getattr(args, 'grad_impl', None) or 'auto'
+        self.grad_kernels = False
+        self._bptt = None
         self._buf = None
         self._graph = None
         self._graph_key = None
@@ -67,6 +73,25 @@ class Trainer(object):
         self.use_xtable = bool(getattr(args, 'encoder_table', True))
         self._xtable = None
         self._xtable_key = None
+        if self.record_for_grad and self.grad_impl in ('auto', 'kernels'):
+            ok = self._bptt_supported()
+            if self.grad_impl == 'kernels' and not ok:
+                raise NotImplementedError("grad_impl='kernels' needs the tensor-core policy path (hid_size 128), the "
+                                          "per-position encoder table, <= 7 action logits and a small vision window")
+            self.grad_kernels = ok
+        if self.grad_impl == 'auto':
+            self.grad_impl = 'kernels' if self.grad_kernels else 'autograd'
+
+    def _bptt_supported(self):
+        e, net = self.env.env, self.policy_net
+        W = 2 * e.vision + 1
+        if net.policy_impl != 'tc' or not self.use_xtable or W * W > 25 or 1 + sum(self.args.naction_heads) > 8:
+            return False
+        if getattr(e, 'obs_layout', (0, 0, 0))[1] == 0:
+            return False
+        npos = e.obs_positions
+        used = npos + ((W * W + 4) if self.is_tj else (2 * W * W + 1))
+        return (used + 15) // 16 * 16 <= 512
 
     def _encoder_table(self, cfg, w):
         """[positions, H] class part of x per agent position for the CURRENT weights (None when not applicable)."""
@@ -100,9 +125,20 @@ class Trainer(object):
                  stat_episodes=z(B, dtype=torch.int32), stat_steps=z(B, dtype=torch.int32),
                  err=z(1, dtype=torch.int32), halted=z(B, dtype=torch.uint8), valid=z(T, B, dtype=torch.uint8),
                  statvec=z(4 + 2 * N, dtype=torch.float64))
-        if self.obs_mode == 'dense' or (self.record_for_grad and self.is_tj):
+        if self.obs_mode == 'dense' or (self.record_for_grad and self.is_tj and not self.grad_kernels):
             b['obs'] = torch.empty(B, N, self.env.observation_dim, dtype=torch.float32, device=dev)
-        if self.record_for_grad:
+        if self.record_for_grad and self.grad_kernels:
+            # hand-written BPTT (csrc/bptt_tc.cu): every step's (h, c) -- the policy step writes them straight into
+            # the record, rec_h[t] -> rec_h[t + 1] -- and the inputs / env state each observation was taken from
+            b.update(s_fresh=z(T, B, dtype=torch.uint8), s_comm=z(T, B, N, dtype=torch.uint8),
+                     s_alive=z(T, B, N, dtype=torch.uint8), s_tep=z(T, B, dtype=torch.int32),
+                     rec_h=torch.empty(T + 1, B * N, H, device=dev), rec_c=torch.empty(T + 1, B * N, H, device=dev))
+            if self.is_tj:
+                b.update(s_tjloc=z(T, B, N, 2, dtype=torch.int32), s_tjalive=z(T, B, N, dtype=torch.uint8),
+                         s_tjlast=z(T, B, N, dtype=torch.uint8), s_tjroute=z(T, B, N, dtype=torch.int32))
+            else:
+                b['s_loc'] = z(T, B, N + 1, 2, dtype=torch.int32)
+        elif self.record_for_grad:
             # inputs of every policy step + (h, c) checkpoints at the window starts
             W = self.grad_window
             nw = (T + W - 1) // W
@@ -145,7 +181,7 @@ class Trainer(object):
 
     def _fused_x(self):
         """Index-form observations on the tensor-core policy path: the encoder runs inside the policy step."""
-        dense = self.obs_mode == 'dense' or (self.record_for_grad and self.is_tj)
+        dense = self.obs_mode == 'dense' or (self.record_for_grad and self.is_tj and not self.grad_kernels)
         W = 2 * self.env.env.vision + 1
         return (not dense) and self.policy_net.policy_impl == 'tc' and W * W <= 25
 
@@ -164,7 +200,8 @@ class Trainer(object):
         s = _lib.stream()
         ws, _ = net.workspace(B)          # tensor-core path scratch (None for the fp32 SIMT kernel)
         rec = self.record_for_grad
-        dense = self.obs_mode == 'dense' or (rec and self.is_tj)
+        gk = rec and self.grad_kernels
+        dense = self.obs_mode == 'dense' or (rec and self.is_tj and not gk)
         # tensor-core path: the index encoder is fused into the policy step (x never leaves the operand image)
         fused_x = self._fused_x()
         src = {}
@@ -180,7 +217,12 @@ class Trainer(object):
                 b['s_tep'][t].copy_(b['t_ep'])
                 if not self.is_tj:
                     b['s_loc'][t].copy_(e.loc)
-                if t % self.grad_window == 0:
+                elif gk:
+                    b['s_tjloc'][t].copy_(e.car_loc)
+                    b['s_tjalive'][t].copy_(e.alive_mask)
+                    b['s_tjlast'][t].copy_(e.car_last_act)
+                    b['s_tjroute'][t].copy_(e.route_id)
+                if not gk and t % self.grad_window == 0:
                     b['ck_h'][t // self.grad_window].copy_(b['h'])
                     b['ck_c'][t // self.grad_window].copy_(b['c'])
             if dense:
@@ -201,10 +243,12 @@ class Trainer(object):
             else:
                 _lib.check(lib.ic3_pp_encoder_index(C.byref(e.cfg), C.byref(e.state), C.byref(cfg), C.byref(w),
                                                     b['x'].data_ptr(), s))
-            io = _lib.PolicyIO(x=None if fused_x else b['x'].data_ptr(), h=b['h'].data_ptr(), c=b['c'].data_ptr(),
+            hin, cin = (b['rec_h'][t], b['rec_c'][t]) if gk else (b['h'], b['c'])
+            hout, cout = (b['rec_h'][t + 1], b['rec_c'][t + 1]) if gk else (b['h'], b['c'])
+            io = _lib.PolicyIO(x=None if fused_x else b['x'].data_ptr(), h=hin.data_ptr(), c=cin.data_ptr(),
                                comm_action=b['comm'].data_ptr() if hard else None, alive=b['alive'].data_ptr(),
                                fresh=b['fresh'].data_ptr(), tick=e.tick.data_ptr(), draws=None,
-                               h_out=b['h'].data_ptr(), c_out=b['c'].data_ptr(), value=b['value'][t].data_ptr(),
+                               h_out=hout.data_ptr(), c_out=cout.data_ptr(), value=b['value'][t].data_ptr(),
                                logp=b['logp'][t].data_ptr(), action=b['action'][t].data_ptr(),
                                workspace=_lib.ptr(ws), err=b['err'].data_ptr(), **src)
             _lib.check(lib.ic3_policy_step(C.byref(cfg), C.byref(w), C.byref(io), s))
@@ -447,10 +491,12 @@ class Trainer(object):
             mean = (adv * v).sum((0, 2), keepdim=True) / cnt
             var = (((adv - mean) * v) ** 2).sum((0, 2), keepdim=True) / (cnt - 1)      # torch.std: unbiased
             adv = (adv - mean) / var.sqrt()
+        if self.grad_kernels:
+            return self._compute_grad_kernels(adv, ret)
         W = self.grad_window
         nw = (T + W - 1) // W
         dh = dc = None
-        if getattr(args, 'grad_impl', 'autograd') == 'manual':
+        if self.grad_impl == 'manual':
             tot = self._compute_grad_manual(adv, ret, W, nw)
             return torch.tensor([tot[k] for k in self.LOSS_KEYS], dtype=torch.float64, device=e.device)
         tot = torch.zeros(3, dtype=torch.float64, device=e.device)
@@ -465,6 +511,79 @@ class Trainer(object):
             dh, dc = h0.grad.detach(), c0.grad.detach()
             tot += torch.stack([st[key] for key in self.LOSS_KEYS]).double()
         return tot
+
+    def _compute_grad_kernels(self, adv, ret):
+        """Hand-written BPTT (csrc/bptt_tc.cu): one ic3_bptt_step per lock-step iteration, last to first; no host
+        synchronisation.  Returns the device float64 vector of the three loss sums."""
+        b, net, args, e = self._buf, self.policy_net, self.args, self.env.env
+        lib = _lib.load()
+        T, B, N, H = b['T'], e.nenvs, args.nagents, args.hid_size
+        s = _lib.stream()
+        cfg = net.policy_cfg(B)
+        cfg.seed, cfg.env_id0 = e.cfg.seed, e.cfg.env_id0
+        w = net.packed()
+        table = self._encoder_table(cfg, w)
+        if self._bptt is None or self._bptt['B'] != B:
+            plan = _lib.BpttPlan(cfg=C.pointer(cfg), w=C.pointer(w),
+                                 pp_env=None if self.is_tj else C.pointer(e.cfg),
+                                 tj_env=C.pointer(e.cfg) if self.is_tj else None, x_table=table.data_ptr(),
+                                 value_coeff=float(args.value_coeff), entr=float(args.entr), workspace=None)
+            nbytes = int(lib.ic3_bptt_workspace_bytes(C.byref(plan)))
+            if nbytes == 0:
+                raise NotImplementedError("this configuration is outside the BPTT kernels (use grad_impl='autograd')")
+            self._bptt = dict(B=B, ws=torch.empty(nbytes, dtype=torch.uint8, device=e.device),
+                              dh=torch.zeros(B * N, H, device=e.device), dc=torch.zeros(B * N, H, device=e.device),
+                              losses=torch.zeros(3, dtype=torch.float64, device=e.device))
+        st = self._bptt
+        plan = _lib.BpttPlan(cfg=C.pointer(cfg), w=C.pointer(w), pp_env=None if self.is_tj else C.pointer(e.cfg),
+                             tj_env=C.pointer(e.cfg) if self.is_tj else None, x_table=table.data_ptr(),
+                             value_coeff=float(args.value_coeff), entr=float(args.entr), workspace=st['ws'].data_ptr())
+        hard = bool(args.hard_attn) and bool(args.commnet)
+        adv = adv.contiguous()
+        cut = None
+        if args.detach_gap <= args.max_steps:                                  # trainer.py:56-60
+            cut = (((b['s_tep'] + 1) % args.detach_gap) == 0).to(torch.uint8).contiguous()
+        lo, hi = torch.aminmax(b['rec_c'][1:])                                  # bound of |c| for the operand scale
+        cmax = max(abs(float(lo.item())), abs(float(hi.item())))
+        st['dh'].zero_()
+        st['dc'].zero_()
+        _lib.check(lib.ic3_bptt_begin(C.byref(plan), cmax, s))
+        value = b['value']
+        for t in reversed(range(T)):
+            io = _lib.BpttStepIO(h_prev=b['rec_h'][t].data_ptr(), c_prev=b['rec_c'][t].data_ptr(),
+                                 h_new=b['rec_h'][t + 1].data_ptr(), fresh=b['s_fresh'][t].data_ptr(),
+                                 comm=b['s_comm'][t].data_ptr() if hard else None, alive=b['s_alive'][t].data_ptr(),
+                                 cut=cut[t].data_ptr() if cut is not None else None,
+                                 pp_loc=None if self.is_tj else b['s_loc'][t].data_ptr(),
+                                 tj_loc=b['s_tjloc'][t].data_ptr() if self.is_tj else None,
+                                 tj_alive=b['s_tjalive'][t].data_ptr() if self.is_tj else None,
+                                 tj_last_act=b['s_tjlast'][t].data_ptr() if self.is_tj else None,
+                                 tj_route_id=b['s_tjroute'][t].data_ptr() if self.is_tj else None,
+                                 logp=b['logp'][t].data_ptr(), action=b['action'][t].data_ptr(),
+                                 value=value[t].data_ptr(), ret=ret[t].data_ptr(), adv=adv[t].data_ptr(),
+                                 alive_post=b['ralive'][t].data_ptr(), valid=b['valid'][t].data_ptr(),
+                                 dh=st['dh'].data_ptr(), dc=st['dc'].data_ptr(), err=b['err'].data_ptr())
+            _lib.check(lib.ic3_bptt_step(C.byref(plan), C.byref(io), s))
+        # parameter gradients are ADDED to the .grad buffers (flat views of FlatRMSprop)
+        params, grads = self._param_structs()
+        _lib.check(lib.ic3_bptt_finish(C.byref(plan), C.byref(params), C.byref(grads), st['losses'].data_ptr(), s))
+        return st['losses']
+
+    def _param_structs(self):
+        """ic3_policy_params of the parameters and of their gradient buffers (reference layouts)."""
+        net = self.policy_net
+        ps = net._param_list()
+        for p in ps:
+            if p.grad is None:
+                p.grad = torch.zeros_like(p)
+
+        def mk(get):
+            hw = (C.c_void_p * _lib.MAX_HEADS)(*([get(h.weight) for h in net.heads] + [None] * (_lib.MAX_HEADS - len(net.heads))))
+            hb = (C.c_void_p * _lib.MAX_HEADS)(*([get(h.bias) for h in net.heads] + [None] * (_lib.MAX_HEADS - len(net.heads))))
+            return _lib.PolicyParams(encoder_w=get(ps[0]), encoder_b=get(ps[1]), c_w=get(ps[2]), c_b=get(ps[3]),
+                                     w_ih=get(ps[4]), w_hh=get(ps[5]), b_ih=get(ps[6]), b_hh=get(ps[7]),
+                                     value_w=get(ps[8]), value_b=get(ps[9]), head_w=hw, head_b=hb)
+        return mk(lambda p: p.data_ptr()), mk(lambda p: p.grad.data_ptr())
 
     def _compute_grad_manual(self, adv, ret, W, nw):
         """``args.grad_impl == 'manual'``: the same gradient from the explicit backward formulas of bptt.py (no autograd

@@ -49,7 +49,11 @@ enum {
 enum {
   IC3_ERR_EPISODE_DONE = 1, /* step() on a finished episode */
   IC3_ERR_ROUTE_OVERRUN = 2,
-  IC3_ERR_BAD_ACTION = 4    /* action > naction (reference asserts, :137 / :228) */
+  IC3_ERR_BAD_ACTION = 4,   /* action > naction (reference asserts, :137 / :228) */
+  IC3_ERR_PIPELINE = 0x100, /* tcgen05 path: an mbarrier wait ran into its watchdog (mis-programmed pipeline) */
+  IC3_ERR_FP16_RANGE = 0x200 /* tcgen05 path: an activation (|a| >= 4094) or folded weight (|w| >= 255) left the range of
+                               the fp16 hi/lo operand split; results of that step are not trustworthy -> use the
+                               fp32 SIMT kernels (policy_impl = 'simt') for such a model */
 };
 
 enum { IC3_PP_MIXED = 0, IC3_PP_COOPERATIVE = 1, IC3_PP_COMPETITIVE = 2 };
@@ -235,6 +239,8 @@ typedef struct {
    * bias_cat: [4H] b_ih + b_hh + W_ih.c_b, column 4*u+gate. */
   void* lstm_img;
   float* bias_cat;
+  int32_t* flags;  /* device word written by ic3_policy_pack (IC3_ERR_FP16_RANGE when a folded weight does not fit the
+                      operand split), OR-ed into ic3_policy_io.err by every policy step; may be NULL */
 } ic3_policy_packed;
 
 #define IC3_LSTM_IMG_BYTES 1572864
@@ -317,6 +323,67 @@ int ic3_returns_scan(int32_t T, int32_t B, int32_t N, float gamma, float mean_ra
 int ic3_stat_reduce(int32_t B, int32_t N, const int32_t* stat_episodes, const int32_t* stat_steps,
                     const int32_t* stat_success, const int32_t* err, const float* stat_reward,
                     const float* stat_comm, double* out, void* stream);
+
+/* ------------------------------------------------------------------------
+ * Back-propagation through time of the rollout loss (Trainer.compute_grad, trainer.py:128-225;
+ * utils.multinomials_log_density utils.py:42-46) over the records of a lock-step rollout, hid_size 128,
+ * at most 7 action logits.  The host walks the lock-step iterations t = T-1 .. 0:
+ *     ic3_bptt_begin(plan, max |c| of the record, stream)
+ *     for t in reversed(range(T)): ic3_bptt_step(plan, &io_t, stream)
+ *     ic3_bptt_finish(plan, params, grads, losses, stream)
+ * Per step: d loss / d (value, logits) from the recorded log-probs / actions / advantages / masks, LSTM cell and
+ * comm backward, and the three GEMMs (gate re-computation, d gates . W, (d gates)^T . features) on the tensor cores
+ * with the forward's fp16 hi/lo operand split.  Parameter gradients are ADDED to the `grads` buffers (the caller
+ * zeroes them, trainer.py:248) and are not divided by num_steps (trainer.py:251-253 does that).
+ * ---------------------------------------------------------------------- */
+typedef struct {
+  const ic3_policy_cfg* cfg;    /* HOST pointers: same structs the rollout used */
+  const ic3_policy_packed* w;
+  const ic3_pp_cfg* pp_env;     /* exactly one of pp_env / tj_env */
+  const ic3_tj_cfg* tj_env;
+  const float* x_table;         /* device: ic3_*_encoder_table of the CURRENT weights (required) */
+  float value_coeff;            /* args.value_coeff (trainer.py:209) */
+  float entr;                   /* args.entr (trainer.py:211-220) */
+  void* workspace;              /* device scratch of ic3_bptt_workspace_bytes(plan) bytes */
+} ic3_bptt_plan;
+
+typedef struct {
+  /* state entering / leaving policy step t */
+  const float* h_prev;          /* [B*N, H] h_{t-1} as fed to the step (ignored for fresh slots) */
+  const float* c_prev;          /* [B*N, H] */
+  const float* h_new;           /* [B*N, H] h'_t */
+  /* inputs of policy step t as recorded */
+  const uint8_t* fresh;         /* [B] */
+  const uint8_t* comm;          /* [B, N] info['comm_action'] (required with hard_attn) */
+  const uint8_t* alive;         /* [B, N] info['alive_mask'] or NULL */
+  const uint8_t* cut;           /* [B] or NULL: (h', c') of step t were detached, (t_ep + 1) % detach_gap == 0 (trainer.py:56-60) */
+  /* environment state the observation of step t was taken from */
+  const int32_t* pp_loc;        /* [B, N+1, 2] */
+  const int32_t* tj_loc;        /* [B, N, 2] */
+  const uint8_t* tj_alive;      /* [B, N] */
+  const uint8_t* tj_last_act;   /* [B, N] */
+  const int32_t* tj_route_id;   /* [B, N] */
+  /* outputs of step t and their learning signals */
+  const float* logp;            /* [B*N, sum(na)] */
+  const int32_t* action;        /* [B*N, nheads] */
+  const float* value;           /* [B*N] */
+  const float* ret;             /* [B*N] returns (ic3_returns_scan) */
+  const float* adv;             /* [B*N] advantages (returns - value, optionally normalised, trainer.py:176-180) */
+  const uint8_t* alive_post;    /* [B*N] misc['alive_mask'] of the step (trainer.py:186-190) */
+  const uint8_t* valid;         /* [B] or NULL: 0 = slot had already completed its batch (ic3_rollout_io.rec_valid) */
+  /* recursion: in = d loss / d (h'_t, c'_t) from later steps, out = d loss / d (h_{t-1}, c_{t-1}) */
+  float* dh;                    /* [B*N, H] */
+  float* dc;                    /* [B*N, H] */
+  int32_t* err;                 /* device flag word (IC3_ERR_PIPELINE / IC3_ERR_FP16_RANGE), may be NULL */
+} ic3_bptt_step_io;
+
+uint64_t ic3_bptt_workspace_bytes(const ic3_bptt_plan* plan);   /* 0 = configuration not supported by the kernels */
+int ic3_bptt_begin(const ic3_bptt_plan* plan, float c_abs_max, void* stream);
+int ic3_bptt_step(const ic3_bptt_plan* plan, const ic3_bptt_step_io* io, void* stream);
+/* params: the CURRENT parameters; grads: same struct holding the gradient buffers (reference layouts);
+ * losses: device double[3] = action_loss, value_loss, entropy sums (trainer.py:198-216). */
+int ic3_bptt_finish(const ic3_bptt_plan* plan, const ic3_policy_params* params, const ic3_policy_params* grads,
+                    double* losses, void* stream);
 
 /* ------------------------------------------------------------------------
  * Optimizer step  (trainer.py:21-22 RMSprop(lr, alpha=0.97, eps=1e-6); trainer.py:251-256 and

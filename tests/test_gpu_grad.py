@@ -39,17 +39,17 @@ def test_returns_scan_matches_oracle():
 
 
 @pytest.mark.parametrize("name", golden_names("grad_"))
-@pytest.mark.parametrize("impl", ["tc", "simt"])
-def test_compute_grad_matches_oracle(name, impl):
+@pytest.mark.parametrize("impl,grad_impl", [("tc", "kernels"), ("tc", "autograd"), ("tc", "manual"), ("simt", "autograd")])
+def test_compute_grad_matches_oracle(name, impl, grad_impl):
     from ic3net_b200 import data
     from ic3net_b200.comm import CommNetMLP
     from ic3net_b200.trainer import Trainer
     meta, z = load_golden(name)
     B, seed, id0 = 5, 808, 30
     args = ns(meta["args"], nenvs=B, seed=seed, env_id0=id0, obs_mode="index", use_graph=False, policy_impl=impl,
-              record_for_grad=True, grad_window=16)
+              record_for_grad=True, grad_window=16, grad_impl=grad_impl)
     if impl == "tc" and args.hid_size != 128:
-        pytest.skip("tensor-core path is specialised for hid_size 128")
+        pytest.skip("tensor-core path (and the BPTT kernels) are specialised for hid_size 128")
     env = data.init(args.env_name, args)
     finish_args(args, env)
     net = CommNetMLP(args, args.num_inputs)
@@ -93,7 +93,9 @@ def test_compute_grad_matches_oracle(name, impl):
         err = np.abs(cpu(prm.grad) - want[key]).max() / np.abs(want[key]).max()
         worst = max(worst, err)
         assert err < 2e-3, (name, key, err)
-    print(name, impl, "worst relative gradient error %.2e" % worst)
+    assert tr.grad_kernels == (grad_impl == "kernels")
+    print(name, impl, grad_impl, "worst relative gradient error %.2e" % worst)
+    assert worst < (1e-4 if grad_impl == "kernels" else 2e-3)
 
 
 def test_train_batch_updates_parameters():
@@ -118,8 +120,9 @@ def test_train_batch_updates_parameters():
     assert 64 * args.batch_size <= stat2["num_steps"] <= 64 * tr.steps_per_batch()
 
 
+@pytest.mark.parametrize("grad_impl", ["auto", "autograd"])
 @pytest.mark.parametrize("name", golden_names("grad_"))
-def test_run_batch_boundary_and_gradient_match_the_reference(name):
+def test_run_batch_boundary_and_gradient_match_the_reference(name, grad_impl):
     """SURVEY a20 / f-1 against numbers the UNMODIFIED reference produced: the fixture is one reference worker
     (`Trainer.run_batch` + `compute_grad`, trainer.py:227-242,128-225) whose draws were routed to the Philox streams
     of (seed, env_id).  One GPU slot with the same streams must stop at the same batch boundary (whole episodes
@@ -129,7 +132,7 @@ def test_run_batch_boundary_and_gradient_match_the_reference(name):
     from ic3net_b200.trainer import Trainer
     meta, z = load_golden(name)
     args = ns(meta["args"], nenvs=1, seed=meta["seed"], env_id0=meta["env_id"], obs_mode="index", use_graph=False,
-              record_for_grad=True, grad_window=16)
+              record_for_grad=True, grad_window=16, grad_impl=grad_impl)
     env = data.init(args.env_name, args)
     finish_args(args, env)
     net = CommNetMLP(args, args.num_inputs)
