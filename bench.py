@@ -512,7 +512,7 @@ def train_leg(opts, build, MultiGPUTrainer, world, dev, dist, torch):
     the reference batch boundary, compute_grad, ONE all-reduce of the flat gradient buffer + the statistics vector,
     RMSprop) -- the like-for-like of the reference's MultiProcessTrainer.train_batch."""
     a, env, net, tr = build("index", opts.train_envs or None, record_for_grad=True, batch_size=opts.train_batch_size,
-                            grad_impl=opts.grad_impl, value_coeff=0.01, entr=0.0, gamma=1.0, normalize_rewards=False,
+                            grad_impl=opts.grad_impl, batch_boundary=opts.train_boundary, value_coeff=0.01, entr=0.0, gamma=1.0, normalize_rewards=False,
                             detach_gap=10000, grad_window=opts.grad_window)
     mgt = MultiGPUTrainer(a, lambda: tr)
     N = a.nagents
@@ -546,7 +546,7 @@ def train_leg(opts, build, MultiGPUTrainer, world, dev, dist, torch):
     return dict(value=steps * N / (tot_ms * 1e-3), unit="agent-env-steps/s", updates=opts.train_updates,
                 envs_per_gpu=a.nenvs, batch_size=a.batch_size, lock_steps_per_update=T,
                 ms_per_update=tot_ms / opts.train_updates, rollout_ms=roll_ms,
-                grad_reduce_step_ms=tot_ms / opts.train_updates - roll_ms, grad_impl=opts.grad_impl,
+                grad_reduce_step_ms=tot_ms / opts.train_updates - roll_ms, grad_impl=tr.grad_impl,
                 replica_max_abs_diff=mgt.replica_checksum(), collectives_per_update=mgt.collectives / max(1, opts.train_updates + 1)
                 if world > 1 else 0,
                 api="MultiGPUTrainer.train_batch (all ranks; device time, max over ranks)")
@@ -737,7 +737,9 @@ def main():
     ap.add_argument("--train_updates", type=int, default=2, help="timed MultiGPUTrainer.train_batch updates (0 = skip)")
     ap.add_argument("--train_envs", type=int, default=0, help="env slots per GPU of the train_batch leg (0 = workload's)")
     ap.add_argument("--train_batch_size", type=int, default=500, help="--batch_size of the train_batch leg (reference default)")
-    ap.add_argument("--grad_impl", default="autograd", choices=["autograd", "manual", "kernels"])
+    ap.add_argument("--grad_impl", default="auto", choices=["auto", "autograd", "manual", "kernels"],
+                    help="compute_grad implementation of the train_batch leg (auto = the Trainer default: the BPTT kernels)")
+    ap.add_argument("--train_boundary", default="reference", choices=["reference", "cut"])
     ap.add_argument("--grad_window", type=int, default=40)
     ap.add_argument("--quick", action="store_true", help="skip the e2e / index / CPU / train legs (profiling runs)")
     ap.add_argument("--skip", default="", help="comma list of legs to skip: train,e2e,kernels,index,cpu")

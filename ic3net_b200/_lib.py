@@ -90,7 +90,7 @@ class BpttPlan(C.Structure):
 
 
 class BpttStepIO(C.Structure):
-    _fields_ = [("h_prev", _p), ("c_prev", _p), ("h_new", _p), ("fresh", _p), ("comm", _p), ("alive", _p), ("cut", _p),
+    _fields_ = [("t", C.c_int32), ("reserved0", C.c_int32), ("h_prev", _p), ("c_prev", _p), ("h_new", _p), ("fresh", _p), ("comm", _p), ("alive", _p), ("cut", _p),
                 ("pp_loc", _p), ("tj_loc", _p), ("tj_alive", _p), ("tj_last_act", _p), ("tj_route_id", _p),
                 ("logp", _p), ("action", _p), ("value", _p), ("ret", _p), ("adv", _p), ("alive_post", _p),
                 ("valid", _p), ("dh", _p), ("dc", _p), ("err", _p)]

@@ -38,9 +38,8 @@ struct BpttScalars {      // device-resident scalars of the recursion
   unsigned dcmax;
   unsigned hbound;        // bound of the heads' contribution to |dh| at the current step
   float cmax;             // max |c| over the whole record (set by the host once per compute_grad)
-  float scale;            // s_t
-  float inv_scale;        // 1 / s_t
-  int pad[2];
+  float scale[2];         // s_t, indexed by t & 1: the weight-gradient kernel of step t runs on a side stream while
+  float inv_scale[2];     // 1 / s_t          the main stream already prepares step t - 1
 };
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -68,7 +67,7 @@ struct HeadsArgs {
 constexpr int HB_ROWS = 256;   // rows per block of the heads kernel
 
 __global__ void __launch_bounds__(256) bptt_heads_kernel(HeadsArgs a) {
-  __shared__ float s_dout[HB_ROWS][BP_HEADS];
+  __shared__ __align__(16) float s_dout[HB_ROWS][BP_HEADS];
   __shared__ float s_wmax[BP_HEADS];
   __shared__ double s_red[8][BP_HEADS + 3];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -148,10 +147,25 @@ __global__ void __launch_bounds__(256) bptt_heads_kernel(HeadsArgs a) {
 #pragma unroll
   for (int o = 0; o < BP_HEADS; ++o) acc[o] = 0.f;
   const int r0 = blockIdx.x * HB_ROWS + half * (HB_ROWS / 2);
-  for (int r = 0; r < HB_ROWS / 2; ++r) {
-    const int rr = r0 + r;
-    if (rr >= a.R) break;
-    const float hv = __ldg(a.h_new + (size_t)rr * TC_H + u);
+  const int nr = min(HB_ROWS / 2, a.R - r0);                 // rows of this half that exist (<= 0: none)
+  const float* hp = a.h_new + (size_t)r0 * TC_H + u;
+  int r = 0;
+  for (; r + 8 <= nr; r += 8) {                               // 8 independent loads in flight per thread
+    float hv[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) hv[q] = __ldg(hp + (size_t)(r + q) * TC_H);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const float4 d0 = *reinterpret_cast<const float4*>(&s_dout[half * (HB_ROWS / 2) + r + q][0]);
+      const float4 d1 = *reinterpret_cast<const float4*>(&s_dout[half * (HB_ROWS / 2) + r + q][4]);
+      acc[0] = fmaf(d0.x, hv[q], acc[0]); acc[1] = fmaf(d0.y, hv[q], acc[1]);
+      acc[2] = fmaf(d0.z, hv[q], acc[2]); acc[3] = fmaf(d0.w, hv[q], acc[3]);
+      acc[4] = fmaf(d1.x, hv[q], acc[4]); acc[5] = fmaf(d1.y, hv[q], acc[5]);
+      acc[6] = fmaf(d1.z, hv[q], acc[6]); acc[7] = fmaf(d1.w, hv[q], acc[7]);
+    }
+  }
+  for (; r < nr; ++r) {
+    const float hv = __ldg(hp + (size_t)r * TC_H);
     const float* dr = s_dout[half * (HB_ROWS / 2) + r];
 #pragma unroll
     for (int o = 0; o < BP_HEADS; ++o) acc[o] = fmaf(dr[o], hv, acc[o]);
@@ -170,7 +184,7 @@ __global__ void __launch_bounds__(256) bptt_heads_kernel(HeadsArgs a) {
 }
 
 // s_t = 2^e with  bound * s_t in (2^13, 2^14]:  |d gate| <= (|dc| + |dh|) * max(1, |c_prev| / 4)
-__global__ void bptt_scale_kernel(BpttScalars* sc) {
+__global__ void bptt_scale_kernel(BpttScalars* sc, int q) {
   const float dh = __uint_as_float(sc->dhmax) + __uint_as_float(sc->hbound);
   const float dc = __uint_as_float(sc->dcmax);
   const float bound = (dh + dc) * fmaxf(1.f, 0.25f * sc->cmax);
@@ -182,8 +196,8 @@ __global__ void bptt_scale_kernel(BpttScalars* sc) {
     e = e > 100 ? 100 : (e < -100 ? -100 : e);
     s = ldexpf(1.f, e);
   }
-  sc->scale = s;
-  sc->inv_scale = 1.f / s;
+  sc->scale[q] = s;
+  sc->inv_scale[q] = 1.f / s;
   sc->dhmax = 0u;
   sc->dcmax = 0u;
   sc->hbound = 0u;
@@ -202,6 +216,7 @@ struct GatesArgs {
   float* dc;                // [R, H] in: d loss / d c'_t;  out: d loss / d c_{t-1}
   __half* dg_img;           // d gates image
   BpttScalars* sc;
+  int q;                    // t & 1
   int32_t* err;
 };
 
@@ -233,15 +248,17 @@ __device__ __forceinline__ float tanh_fwd(float c) {      // tanh(c') as the for
   return fmaf(2.f, rcp_fast(b), -1.f);
 }
 
+// 8 values -> hi / lo fp16 halves (x * scale = hi + lo), two values per conversion instruction
 __device__ __forceinline__ uint4 pack8_hi_lo(const float (&x)[8], float scale, uint4& lo) {
   uint32_t h[4], l[4];
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
-    __half h0, l0, h1, l1;
-    split_f16(x[2 * j], scale, h0, l0);
-    split_f16(x[2 * j + 1], scale, h1, l1);
-    h[j] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
-    l[j] = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
+    const float a = x[2 * j] * scale, b = x[2 * j + 1] * scale;       // power of two: exact
+    const __half2 hh = __floats2half2_rn(a, b);
+    const float2 hf = __half22float2(hh);
+    const __half2 ll = __floats2half2_rn(a - hf.x, b - hf.y);
+    h[j] = *reinterpret_cast<const uint32_t*>(&hh);
+    l[j] = *reinterpret_cast<const uint32_t*>(&ll);
   }
   lo = make_uint4(l[0], l[1], l[2], l[3]);
   return make_uint4(h[0], h[1], h[2], h[3]);
@@ -342,7 +359,7 @@ __global__ void __launch_bounds__(TC_P_THREADS, 1) bptt_gates_kernel(GatesArgs g
   } else if (warp < EPI_WARPS) {
     // ===== epilogue: thread = (row of the tile, 16 hidden units) =====
     const int quarter = warp & 3, cq = warp >> 2;
-    const float scale = g.sc->scale;
+    const float scale = g.sc->scale[g.q];
     uint32_t li = 0;
     bool ok = true;
     float dcm = 0.f;
@@ -368,12 +385,25 @@ __global__ void __launch_bounds__(TC_P_THREADS, 1) bptt_gates_kernel(GatesArgs g
         dsum[0] = d0.x; dsum[1] = d0.y; dsum[2] = d0.z; dsum[3] = d0.w;
         dsum[4] = d1.x; dsum[5] = d1.y; dsum[6] = d1.z; dsum[7] = d1.w;
       }
+      // c_{t-1}, dh, dc of the first 4 hidden units: in flight while the MMAs of this item finish
+      const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+      const bool ld_c = inrange && !fr, ld_d = inrange && !ct;
+      const size_t rbase = (size_t)row * TC_H + ubase;
+      float4 cp_n = ld_c ? *reinterpret_cast<const float4*>(g.c_prev + rbase) : z4;
+      float4 dh_n = ld_d ? *reinterpret_cast<const float4*>(g.dh + rbase) : z4;
+      float4 dc_n = ld_d ? *reinterpret_cast<const float4*>(g.dc + rbase) : z4;
       if (ok) ok = mbar_wait(bar_tfull + 8 * acc, (li >> 1) & 1, g.err);
       tc_fence_after();
       const uint32_t taddr = tmem_base + acc * TC_NH + cq * 64 + ((uint32_t)(quarter * 32) << 16);
       __half* img_row = g.dg_img + (size_t)tile * DG_TILE_HALFS + (size_t)((quarter * 4 + (lane >> 3)) * 64 + (lane & 7) * 8);
 #pragma unroll
       for (int q4 = 0; q4 < 4; ++q4) {        // 4 hidden units (16 accumulator columns = 2 column groups) at a time
+        const float4 cp = cp_n, dhv = dh_n, dcv = dc_n;
+        if (q4 < 3) {                          // next group's operands: issued before this group's math
+          cp_n = ld_c ? *reinterpret_cast<const float4*>(g.c_prev + rbase + (q4 + 1) * 4) : z4;
+          dh_n = ld_d ? *reinterpret_cast<const float4*>(g.dh + rbase + (q4 + 1) * 4) : z4;
+          dc_n = ld_d ? *reinterpret_cast<const float4*>(g.dc + rbase + (q4 + 1) * 4) : z4;
+        }
         uint32_t v[16];
         tmem_ld16(taddr + q4 * 16, v);
         const int u0 = ubase + q4 * 4;
@@ -383,15 +413,8 @@ __global__ void __launch_bounds__(TC_P_THREADS, 1) bptt_gates_kernel(GatesArgs g
         if (ok && inrange) {
           float gi[4], gf[4], gg[4], go[4];
           gates4(v, s_bias + 4 * u0, gi, gf, gg, go);
-          float4 cp = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (!fr) cp = *reinterpret_cast<const float4*>(g.c_prev + (size_t)row * TC_H + u0);
-          float4 dhv = make_float4(0.f, 0.f, 0.f, 0.f), dcv = dhv;
-          if (!ct) {
-            dhv = *reinterpret_cast<const float4*>(g.dh + (size_t)row * TC_H + u0);
-            dcv = *reinterpret_cast<const float4*>(g.dc + (size_t)row * TC_H + u0);
-          }
           const float cpa[4] = {cp.x, cp.y, cp.z, cp.w};
-          float dha[4] = {dhv.x, dhv.y, dhv.z, dhv.w};
+          const float dha[4] = {dhv.x, dhv.y, dhv.z, dhv.w};
           const float dca[4] = {dcv.x, dcv.y, dcv.z, dcv.w};
           float dcp[4];
 #pragma unroll
@@ -470,6 +493,7 @@ struct DgradArgs {
   float* dSs;            // [R, H]  out: gs * dS
   float* dh_direct;      // [R, H]  out
   const BpttScalars* sc;
+  int q;
   int32_t* err;
 };
 
@@ -556,7 +580,7 @@ __global__ void __launch_bounds__(TC_P_THREADS, 1) bptt_dgrad_kernel(DgradArgs g
     }
   } else if (warp < EPI_WARPS) {
     const int quarter = warp & 3, cq = warp >> 2;
-    const float unscale = g.sc->inv_scale * (1.f / SCALE_B);
+    const float unscale = g.sc->inv_scale[g.q] * (1.f / SCALE_B);
     uint32_t li = 0;
     bool ok = true;
     for (int tile = blockIdx.x; tile < ntiles; tile += ncta, ++li) {
@@ -666,6 +690,7 @@ struct WgradArgs {
   int j0, j1;            // row-tile subsets of slice 0 / slice 1 (4 * (j0 + j1) CTAs)
   float* partial;        // [ncta][512 columns max][128] fp32, CTA-private
   const BpttScalars* sc;
+  int q;
   int32_t* err;
 };
 
@@ -790,7 +815,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) bptt_wgrad_kernel(WgradArgs g, 
       const bool ok = mbar_wait(bar_done, 0, g.err);
       tc_fence_after();
       // slice 0: x|S|h products carry SCALE_A * s_t, slice 1 (P exact) only s_t
-      const float unscale = g.sc->inv_scale * (sl == 0 ? 1.f / SCALE_A : 1.f);
+      const float unscale = g.sc->inv_scale[g.q] * (sl == 0 ? 1.f / SCALE_A : 1.f);
       const int m = warp * 32 + lane;
       for (int c0 = 0; c0 < ncols; c0 += 16) {
         uint32_t v[16];
@@ -1041,8 +1066,32 @@ int sm_count() {
   return n;
 }
 
+// Side stream of the weight-gradient kernel + the events that order it against the main stream (IC3_BPTT_OVERLAP=0
+// keeps everything on the caller's stream).
+struct BpttStreams {
+  cudaStream_t side;
+  cudaEvent_t gates_done[2], wgrad_done[2];
+  bool overlap;
+};
+
+BpttStreams* bptt_streams() {
+  static BpttStreams ss;
+  static int state = 0;      // 0 = not created, 1 = ok, -1 = failed
+  if (state == 0) {
+    const char* e = getenv("IC3_BPTT_OVERLAP");
+    ss.overlap = !(e && atoi(e) == 0);
+    bool ok = cudaStreamCreateWithFlags(&ss.side, cudaStreamNonBlocking) == cudaSuccess;
+    for (int k = 0; k < 2 && ok; ++k) {
+      ok = cudaEventCreateWithFlags(&ss.gates_done[k], cudaEventDisableTiming) == cudaSuccess &&
+           cudaEventCreateWithFlags(&ss.wgrad_done[k], cudaEventDisableTiming) == cudaSuccess;
+    }
+    state = ok ? 1 : -1;
+  }
+  return state == 1 ? &ss : nullptr;
+}
+
 struct Layout {         // of the workspace, in bytes
-  size_t a_img, p_img, dg_img, w2_img, dout, dSs, dh_direct, gs, gr, partial, gw_part, gs_part, sc, G, Y, GSC, dC, wj, cw, losses,
+  size_t a_img, p_img, dg_img, img_stride, w2_img, dout, dSs, dh_direct, gs, gr, partial, gw_part, gs_part, sc, G, Y, GSC, dC, wj, cw, losses,
       total;
   int ntiles, np, npos, WW, j0, j1, ncta_wg, nhb;
 };
@@ -1068,9 +1117,13 @@ int plan_layout(const ic3_policy_cfg* cfg, int npos, int WW, int is_tj, Layout* 
   L->nhb = (int)((R + HB_ROWS - 1) / HB_ROWS);
   size_t off = 0;
   auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 1023) / 1024 * 1024; return o; };
+  // two sets of operand images (step parity): the weight-gradient kernel of step t reads set t & 1 on the side stream
+  // while the main stream fills the other set for step t - 1
   L->a_img = take((size_t)L->ntiles * A_TILE_HALFS * 2);
   L->p_img = take((size_t)L->ntiles * (L->np / 8) * 16 * 128);
   L->dg_img = take((size_t)L->ntiles * DG_TILE_HALFS * 2);
+  L->img_stride = off;
+  take(off);                                   // second set: same sizes, same order
   L->w2_img = take(W2_IMG_HALFS * 2);
   L->dout = take((size_t)L->ntiles * TC_M * BP_HEADS * 4);
   L->dSs = take((size_t)L->ntiles * TC_M * TC_H * 4);
@@ -1138,9 +1191,7 @@ extern "C" int ic3_bptt_begin(const ic3_bptt_plan* p, float cmax, void* stream) 
   unsigned char* ws = reinterpret_cast<unsigned char*>(p->workspace);
   cudaError_t e = cudaMemsetAsync(ws + L.partial, 0, L.total - L.partial, s);   // partial .. end: all accumulators / scalars
   if (e != cudaSuccess) return (int)e;
-  e = cudaMemsetAsync(ws + L.a_img, 0, L.dg_img - L.a_img, s);                  // padding rows of the images stay zero
-  if (e != cudaSuccess) return (int)e;
-  e = cudaMemsetAsync(ws + L.dg_img, 0, L.w2_img - L.dg_img, s);
+  e = cudaMemsetAsync(ws + L.a_img, 0, L.w2_img - L.a_img, s);                  // both image sets
   if (e != cudaSuccess) return (int)e;
   bptt_pack_w2_kernel<<<(256 * 512 + 255) / 256, 256, 0, s>>>(reinterpret_cast<const __half*>(p->w->lstm_img),
                                                               reinterpret_cast<__half*>(ws + L.w2_img));
@@ -1148,8 +1199,8 @@ extern "C" int ic3_bptt_begin(const ic3_bptt_plan* p, float cmax, void* stream) 
   BpttScalars init;
   memset(&init, 0, sizeof(init));
   init.cmax = cmax;
-  init.scale = 1.f;
-  init.inv_scale = 1.f;
+  init.scale[0] = init.scale[1] = 1.f;
+  init.inv_scale[0] = init.inv_scale[1] = 1.f;
   e = cudaMemcpyAsync(ws + L.sc, &init, sizeof(init), cudaMemcpyHostToDevice, s);
   if (e != cudaSuccess) return (int)e;
   return IC3_OK;
@@ -1176,9 +1227,15 @@ extern "C" int ic3_bptt_step(const ic3_bptt_plan* p, const ic3_bptt_step_io* io,
   const int nout = 1 + atot;
   if (nout > BP_HEADS) return IC3_E_UNSUPPORTED;
   BpttScalars* sc = reinterpret_cast<BpttScalars*>(ws + L.sc);
-  __half* a_img = reinterpret_cast<__half*>(ws + L.a_img);
-  __half* p_img = reinterpret_cast<__half*>(ws + L.p_img);
-  __half* dg_img = reinterpret_cast<__half*>(ws + L.dg_img);
+  const int q = io->t & 1;
+  __half* a_img = reinterpret_cast<__half*>(ws + L.a_img + (size_t)q * L.img_stride);
+  __half* p_img = reinterpret_cast<__half*>(ws + L.p_img + (size_t)q * L.img_stride);
+  __half* dg_img = reinterpret_cast<__half*>(ws + L.dg_img + (size_t)q * L.img_stride);
+  BpttStreams* ss = bptt_streams();
+  if (!ss) return IC3_E_UNSUPPORTED;
+  // image set q was last read by the weight-gradient kernel of step t + 2 (side stream)
+  cudaError_t se = cudaStreamWaitEvent(s, ss->wgrad_done[q], 0);
+  if (se != cudaSuccess) return (int)se;
 
   // ---- heads ----
   HeadsArgs ha;
@@ -1194,7 +1251,7 @@ extern "C" int ic3_bptt_step(const ic3_bptt_plan* p, const ic3_bptt_step_io* io,
   ha.sc = sc;
   bptt_heads_kernel<<<L.nhb, 256, 0, s>>>(ha);
   IC3_LAUNCH_CHECK();
-  bptt_scale_kernel<<<1, 1, 0, s>>>(sc);
+  bptt_scale_kernel<<<1, 1, 0, s>>>(sc, q);
   IC3_LAUNCH_CHECK();
 
   // ---- operand images of step t from the records ----
@@ -1244,12 +1301,15 @@ extern "C" int ic3_bptt_step(const ic3_bptt_plan* p, const ic3_bptt_step_io* io,
     GatesArgs ga;
     ga.R = R; ga.N = cfg->N; ga.c_prev = io->c_prev; ga.fresh = io->fresh; ga.cut = io->cut;
     ga.dout = reinterpret_cast<const float*>(ws + L.dout); ga.dh = io->dh; ga.dc = io->dc; ga.dg_img = dg_img; ga.sc = sc;
+    ga.q = q;
     ga.err = io->err;
     const int nitems = 2 * ntiles;
     const int grid = nitems < sm_count() ? nitems : sm_count();
     bptt_gates_kernel<<<grid, TC_P_THREADS, smem, s>>>(ga, a_img, reinterpret_cast<const __half*>(p->w->lstm_img),
                                                       (const float*)p->w->bias_cat, nitems, (const float*)p->w->head_w, nout);
     IC3_LAUNCH_CHECK();
+    se = cudaEventRecord(ss->gates_done[q], s);
+    if (se != cudaSuccess) return (int)se;
   }
   // ---- dgrad ----
   {
@@ -1262,7 +1322,7 @@ extern "C" int ic3_bptt_step(const ic3_bptt_plan* p, const ic3_bptt_step_io* io,
     }
     DgradArgs da;
     da.R = R; da.gs = reinterpret_cast<const float*>(ws + L.gs); da.dSs = reinterpret_cast<float*>(ws + L.dSs);
-    da.dh_direct = reinterpret_cast<float*>(ws + L.dh_direct); da.sc = sc; da.err = io->err;
+    da.dh_direct = reinterpret_cast<float*>(ws + L.dh_direct); da.sc = sc; da.q = q; da.err = io->err;
     const int grid = ntiles < sm_count() ? ntiles : sm_count();
     bptt_dgrad_kernel<<<grid, TC_P_THREADS, smem, s>>>(da, dg_img, reinterpret_cast<const __half*>(ws + L.w2_img), ntiles);
     IC3_LAUNCH_CHECK();
@@ -1276,10 +1336,10 @@ extern "C" int ic3_bptt_step(const ic3_bptt_plan* p, const ic3_bptt_step_io* io,
     bptt_comm_kernel<<<(cfg->B + 7) / 8, 256, 0, s>>>(ca);
     IC3_LAUNCH_CHECK();
   }
-  // ---- weight gradients ----
+  // ---- weight gradients: on the side stream, overlapping the small kernels of this and the next step ----
   {
     static bool cfgd = false;
-    static CUtensorMap map_dg, map_a, map_p;
+    static CUtensorMap map_dg[2], map_a[2], map_p[2];
     static void* key_ws = nullptr;
     static int key_tiles = 0, key_np = 0;
     const size_t smem1 = (size_t)WG_NSTAGE1 * (2 * WG_DG_BYTES + (size_t)L.np * 64);
@@ -1291,19 +1351,28 @@ extern "C" int ic3_bptt_step(const ic3_bptt_plan* p, const ic3_bptt_step_io* io,
     }
     if (smem > 200 * 1024) return IC3_E_UNSUPPORTED;
     if (key_ws != p->workspace || key_tiles != ntiles || key_np != L.np) {
-      rc = make_image_map(&map_dg, dg_img, ntiles, 2, 64, 16);
-      if (rc) return rc;
-      rc = make_image_map(&map_a, a_img, ntiles, 2, 48, 48);
-      if (rc) return rc;
-      rc = make_image_map(&map_p, p_img, ntiles, 0, L.np / 8, L.np / 8);
-      if (rc) return rc;
+      for (int k = 0; k < 2; ++k) {
+        rc = make_image_map(&map_dg[k], ws + L.dg_img + (size_t)k * L.img_stride, ntiles, 2, 64, 16);
+        if (rc) return rc;
+        rc = make_image_map(&map_a[k], ws + L.a_img + (size_t)k * L.img_stride, ntiles, 2, 48, 48);
+        if (rc) return rc;
+        rc = make_image_map(&map_p[k], ws + L.p_img + (size_t)k * L.img_stride, ntiles, 0, L.np / 8, L.np / 8);
+        if (rc) return rc;
+      }
       key_ws = p->workspace; key_tiles = ntiles; key_np = L.np;
     }
     WgradArgs wa;
     wa.ntiles = ntiles; wa.np = L.np; wa.j0 = L.j0; wa.j1 = L.j1;
-    wa.partial = reinterpret_cast<float*>(ws + L.partial); wa.sc = sc; wa.err = io->err;
-    bptt_wgrad_kernel<<<L.ncta_wg, WG_THREADS, smem, s>>>(wa, map_dg, map_a, map_p);
+    wa.partial = reinterpret_cast<float*>(ws + L.partial); wa.sc = sc; wa.q = q; wa.err = io->err;
+    cudaStream_t ws_stream = ss->overlap ? ss->side : s;
+    if (ss->overlap) {
+      se = cudaStreamWaitEvent(ws_stream, ss->gates_done[q], 0);
+      if (se != cudaSuccess) return (int)se;
+    }
+    bptt_wgrad_kernel<<<L.ncta_wg, WG_THREADS, smem, ws_stream>>>(wa, map_dg[q], map_a[q], map_p[q]);
     IC3_LAUNCH_CHECK();
+    se = cudaEventRecord(ss->wgrad_done[q], ws_stream);
+    if (se != cudaSuccess) return (int)se;
   }
   return IC3_OK;
 }
@@ -1322,6 +1391,12 @@ extern "C" int ic3_bptt_finish(const ic3_bptt_plan* p, const ic3_policy_params* 
   if (rc) return rc;
   cudaStream_t s = (cudaStream_t)stream;
   unsigned char* ws = reinterpret_cast<unsigned char*>(p->workspace);
+  if (BpttStreams* ss = bptt_streams()) {       // the last weight-gradient kernels may still run on the side stream
+    for (int k = 0; k < 2; ++k) {
+      cudaError_t e = cudaStreamWaitEvent(s, ss->wgrad_done[k], 0);
+      if (e != cudaSuccess) return (int)e;
+    }
+  }
   const int NC = 384 + L.np;
   double* G = reinterpret_cast<double*>(ws + L.G);
   double* Y = reinterpret_cast<double*>(ws + L.Y);

@@ -550,7 +550,7 @@ class Trainer(object):
         _lib.check(lib.ic3_bptt_begin(C.byref(plan), cmax, s))
         value = b['value']
         for t in reversed(range(T)):
-            io = _lib.BpttStepIO(h_prev=b['rec_h'][t].data_ptr(), c_prev=b['rec_c'][t].data_ptr(),
+            io = _lib.BpttStepIO(t=t, h_prev=b['rec_h'][t].data_ptr(), c_prev=b['rec_c'][t].data_ptr(),
                                  h_new=b['rec_h'][t + 1].data_ptr(), fresh=b['s_fresh'][t].data_ptr(),
                                  comm=b['s_comm'][t].data_ptr() if hard else None, alive=b['s_alive'][t].data_ptr(),
                                  cut=cut[t].data_ptr() if cut is not None else None,

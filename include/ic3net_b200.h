@@ -348,6 +348,8 @@ typedef struct {
 } ic3_bptt_plan;
 
 typedef struct {
+  int32_t t;                    /* lock-step index (its parity selects the operand-image set of the step) */
+  int32_t reserved0;
   /* state entering / leaving policy step t */
   const float* h_prev;          /* [B*N, H] h_{t-1} as fed to the step (ignored for fresh slots) */
   const float* c_prev;          /* [B*N, H] */

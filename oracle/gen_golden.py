@@ -606,7 +606,27 @@ def gen_log_case(name="log_contract"):
         json.dump(out, f, indent=0)
 
 
+def gen_hid128_grad_cases():
+    """Gradient fixtures at hid_size 128 (the shape the tensor-core rollout and the BPTT kernels run at) covering the
+    loss / comm variants: entropy bonus, normalised advantages, cooperative returns, comm_mode sum, plain CommNet (no
+    hard attention), vision-1 windows with count features, IC-style comm_mask_zero."""
+    gen_grad_case("grad_pp_v1_commnet_entr_h128", 65, 3, 75, env_name="predator_prey", nagents=4, dim=6, vision=1,
+                  max_steps=15, hid_size=128, commnet=True, batch_size=40, mode="cooperative", entr=0.01,
+                  mean_ratio=1.0, gamma=0.95, normalize_rewards=True)
+    gen_grad_case("grad_tj_easy_commnet_sum_h128", 66, 1, 76, env_name="traffic_junction", nagents=5, dim=6, vision=0,
+                  max_steps=20, hid_size=128, commnet=True, comm_mode="sum", difficulty="easy", add_rate_min=0.3,
+                  add_rate_max=0.3, batch_size=50, mean_ratio=0.5, gamma=0.9, entr=0.005)
+    gen_grad_case("grad_tj_medium_v1_ic_h128", 67, 2, 77, env_name="traffic_junction", nagents=6, dim=14, vision=1,
+                  max_steps=30, hid_size=128, ic3net=True, comm_mask_zero=True, difficulty="medium",
+                  add_rate_min=0.25, add_rate_max=0.25, batch_size=45, detach_gap=7)
+
+
 def main():
+    if "--grad128-only" in sys.argv:
+        import warnings
+        warnings.filterwarnings("ignore")
+        gen_hid128_grad_cases()
+        return 0
     if "--log-only" in sys.argv:
         gen_log_case()
         return 0
@@ -673,6 +693,7 @@ def main():
     gen_grad_case("grad_tj_easy_commnet", 64, 0, 74, env_name="traffic_junction", nagents=5, dim=6, vision=0,
                   max_steps=20, hid_size=64, commnet=True, difficulty="easy", add_rate_min=0.3, add_rate_max=0.3,
                   batch_size=50, mean_ratio=0.5, gamma=0.9)
+    gen_hid128_grad_cases()
     gen_rmsprop_case("rmsprop_ref", 81)
     gen_log_case()
     return 0
