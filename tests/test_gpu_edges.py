@@ -118,3 +118,34 @@ def test_cli_runs_reference_flags(capsys):
                    "--epoch_size", "1", "--batch_size", "20", "--seed", "4", "--difficulty", "easy", "--add_rate_min",
                    "0.3", "--add_rate_max", "0.3", "--rollout_only"])
     assert rc == 0
+
+
+def test_fp16_operand_range_is_flagged_not_silent():
+    """The tensor-core path splits operands into fp16 halves (|activation| < 4094, |folded weight| < 255).  Weights or
+    activations outside that range must raise the device flag (IC3_ERR_FP16_RANGE) -- surfaced as an exception by
+    Trainer.collect_stat -- instead of silently producing inf; the fp32 SIMT path accepts the same model."""
+    from ic3net_b200 import _lib, data
+    from ic3net_b200.comm import CommNetMLP
+    from ic3net_b200.trainer import Trainer
+
+    def run(impl, scale_w=1.0, scale_enc=1.0):
+        args = pp_args(3, 5, 0, 4, policy_impl=impl)
+        env = data.init(args.env_name, args)
+        finish_args(args, env)
+        torch.manual_seed(0)
+        net = CommNetMLP(args, args.num_inputs)
+        with torch.no_grad():
+            net.f_module.weight_hh.mul_(scale_w)
+            net.encoder.weight.mul_(scale_enc)
+        tr = Trainer(args, net, env)
+        tr.rollout(4, 0)
+        return tr
+
+    run("tc").collect_stat()                                             # in range: no flag
+    with pytest.raises(RuntimeError, match="0x200"):                     # |w| * 256 >= 65504
+        run("tc", scale_w=4000.0).collect_stat()
+    with pytest.raises(RuntimeError, match="0x200"):                     # |x| * 16 >= 65504
+        run("tc", scale_enc=1.0e5).collect_stat()
+    tr = run("simt", scale_w=4000.0)                                     # fp32 kernels: same weights are fine
+    tr.collect_stat()
+    assert _lib.ERR_FP16_RANGE == 0x200

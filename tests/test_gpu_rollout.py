@@ -179,3 +179,54 @@ def test_pp_hard_full_size_rollout_properties():
     assert bool((b.episode_mask[-1] == 0).all())                         # batch end cuts every open episode
     assert abs(stat["reward"].sum() - float(r.double().sum())) < 1e-2 * B
     assert torch.isfinite(b.value).all()
+
+
+def replay_slots(args, z, p, batch, slots, T, seed, env_id0):
+    """Teacher-forced oracle replay of the given env slots of a lock-step rollout (cut at T)."""
+    is_tj = args.env_name == "traffic_junction"
+    idx = torch.as_tensor(slots, device=batch.action.device)
+    act, rew = cpu(batch.action[:, idx]), cpu(batch.reward[:, idx])
+    val, lp = cpu(batch.value[:, idx]), cpu(batch.logp[:, idx])
+    emask, mini, alive = cpu(batch.episode_mask[:, idx]), cpu(batch.episode_mini_mask[:, idx]), cpu(batch.alive_mask[:, idx])
+    flips = draws = 0
+    for j, b in enumerate(slots):
+        t0, k = 0, 0
+        orc = make_oracle_env(args, tj_tables(z) if is_tj else None)
+        while t0 < T:
+            ep = run_episode(orc, p, args, seed, env_id0 + b, epoch=0, tick0=t0, episode=k,
+                             forced_actions=act[t0:, j], max_steps=min(args.max_steps, T - t0))
+            L = ep["num_steps"]
+            sl = slice(t0, t0 + L)
+            assert np.array_equal(rew[sl, j], ep["reward"].astype(np.float32)), (b, k)
+            assert np.array_equal(emask[sl, j], ep["emask"][:, 0]) and np.array_equal(mini[sl, j], ep["mini"]), (b, k)
+            assert np.array_equal(alive[sl, j], ep["alive"]), (b, k)
+            assert close(val[sl, j], ep["value"]) and close(lp[sl, j], ep["logp"]), (b, k)
+            own = np.array([opolicy.sample_actions(np.split(ep["logp"][t], np.cumsum(args.naction_heads)[:-1], -1),
+                                                   opolicy.action_draws(seed, env_id0 + b, t0 + t, args.nagents,
+                                                                        len(args.naction_heads)))[0]
+                            for t in range(L)])
+            safe = ep["margin"] > 1e-4
+            assert np.array_equal(own[safe], act[sl, j][safe]), (b, k)
+            flips += int((own != act[sl, j]).sum())
+            draws += own.size
+            t0 += L
+            k += 1
+    assert flips <= 2e-3 * draws
+
+
+@pytest.mark.parametrize("name,B", [("ep_pp_hard_ic3net", 8192), ("ep_tj_hard_ic3net", 4096)])
+def test_full_size_rollout_sampled_slots_match_oracle(name, B):
+    """BASELINE c2 / c5 at their FULL batch sizes: 32 env slots drawn at random -- always including the first slot,
+    the slots that straddle 128-row tile boundaries of the tensor-core kernels and the very last ones -- are replayed
+    step by step through the float64 oracle (bit-exact integers / rewards, 1e-5 on values and log-probs)."""
+    meta, z = load_golden(name)
+    T, seed, id0 = 24, 4242, 1000
+    args, env, net, tr, p = build(meta, B, "index", seed=seed, env_id0=id0)
+    batch = tr.rollout(T, 0)
+    stat = tr.collect_stat()
+    assert stat["num_steps"] == B * T
+    N = args.nagents
+    rs = np.random.RandomState(7)
+    edge = [0, 128 // N, 128 // N + 1, B // 2, B - 2, B - 1, (B * N - 128) // N]       # tile-boundary / tail slots
+    slots = sorted(set(edge) | set(int(x) for x in rs.randint(0, B, size=32 - len(set(edge)))))
+    replay_slots(args, z, p, batch, slots, T, seed, id0)
