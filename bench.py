@@ -239,6 +239,11 @@ def gpu_arm(opts):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    # ONE JSON line on stdout is the contract: libraries that write to file descriptor 1 on their own (NCCL's version
+    # banner) are sent to stderr for the whole run; the result line goes to the saved descriptor at the end.
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
     # Host-side work is a few tiny tensor ops per step; letting torch fan them out over every visible
     # core (128 here, with a 16-core cgroup quota) only earns CPU throttling stalls.  The reference's
     # README asks for OMP_NUM_THREADS=1 as well (README.md:48); torchrun sets the same default.
@@ -500,7 +505,8 @@ def gpu_arm(opts):
             line["fused_index_rollout"] = alt
         if cpu:
             line["cpu_baseline"] = cpu
-        print(json.dumps(line))
+        sys.stdout.flush()
+        os.write(real_stdout, (json.dumps(line) + "\n").encode())
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
