@@ -15,6 +15,8 @@ LIB_PATH = os.path.join(_HERE, "libic3net_b200.so")
 MAX_AGENTS = 32
 MAX_HEADS = 4
 MAX_HEAD_DIM = 16
+MAX_PASSES = 4
+CELL_LSTM, CELL_TANH = 0, 1
 LSTM_IMG_BYTES = 1572864
 
 ERR_EPISODE_DONE = 1
@@ -62,18 +64,20 @@ class PolicyCfg(C.Structure):
     _fields_ = [("B", C.c_int32), ("N", C.c_int32), ("H", C.c_int32), ("O", C.c_int32), ("nheads", C.c_int32),
                 ("head_dim", C.c_int32 * MAX_HEADS), ("hard_attn", C.c_int32), ("comm_avg", C.c_int32),
                 ("comm_mask_zero", C.c_int32), ("env_id0", C.c_uint32), ("seed", C.c_uint64),
-                ("obs_off", C.c_int32), ("obs_vocab", C.c_int32), ("obs_ncount", C.c_int32), ("reserved0", C.c_int32)]
+                ("obs_off", C.c_int32), ("obs_vocab", C.c_int32), ("obs_ncount", C.c_int32), ("cell", C.c_int32),
+                ("passes", C.c_int32), ("x_tanh", C.c_int32), ("h_from_x", C.c_int32), ("reserved0", C.c_int32)]
 
 
 class PolicyParams(C.Structure):
     _fields_ = [("encoder_w", _p), ("encoder_b", _p), ("c_w", _p), ("c_b", _p), ("w_ih", _p), ("w_hh", _p),
                 ("b_ih", _p), ("b_hh", _p), ("value_w", _p), ("value_b", _p),
-                ("head_w", _p * MAX_HEADS), ("head_b", _p * MAX_HEADS)]
+                ("head_w", _p * MAX_HEADS), ("head_b", _p * MAX_HEADS), ("c_w_pass", _p * MAX_PASSES),
+                ("c_b_pass", _p * MAX_PASSES), ("f_w_pass", _p * MAX_PASSES), ("f_b_pass", _p * MAX_PASSES)]
 
 
 class PolicyPacked(C.Structure):
     _fields_ = [("enc_wT", _p), ("enc_b", _p), ("c_wT", _p), ("c_b", _p), ("lstm_wT", _p), ("lstm_b", _p),
-                ("head_w", _p), ("head_b", _p), ("lstm_img", _p), ("bias_cat", _p), ("flags", _p)]
+                ("head_w", _p), ("head_b", _p), ("lstm_img", _p), ("bias_cat", _p), ("f_wT", _p), ("f_b", _p), ("flags", _p)]
 
 
 class PolicyIO(C.Structure):

@@ -6,10 +6,11 @@ surface (comm.py:8-253): ``CommNetMLP(args, num_inputs)``, ``forward(x, info={})
 
 The forward pass runs the hand-written kernels of csrc/policy.cu through the C ABI
 (encoder, gated hidden-state mean, C, LSTMCell, value/action heads) in float32 for a
-whole batch ``[B, N, .]`` of environments.  Only the recurrent (LSTM) branch with
-``comm_passes == 1`` is accelerated -- the branch every BASELINE config uses; other
-variants raise.  The rollout forward is inference-only (the reference detaches what
-it samples from, action_utils.py:35); gradients are taken by the trainer.
+whole batch ``[B, N, .]`` of environments.  The recurrent (LSTM) branch with one comm pass -- the
+branch every BASELINE config uses -- runs on the tcgen05 kernels; ``comm_passes > 1``,
+``share_weights`` and the non-recurrent tanh branch (comm.py:63-70,127-131,220-224) run on the
+fp32 SIMT kernel.  The rollout forward is inference-only (the reference detaches what it samples
+from, action_utils.py:35); gradients are taken by the trainer.
 """
 import ctypes as C
 
@@ -35,6 +36,48 @@ def _as_u8(v, B, N, device):
 
 
 class CommNetMLP(nn.Module):
+    # kernel-side description of the variant (include/ic3net_b200.h, ic3_policy_cfg.cell / passes / x_tanh / h_from_x)
+    def _variant(self, args):
+        rec = bool(args.recurrent)
+        return dict(cell=_lib.CELL_LSTM if rec else _lib.CELL_TANH, passes=int(args.comm_passes),
+                    x_tanh=0 if rec else 1, h_from_x=0 if rec else 1)
+
+    def _build_modules(self, args, num_inputs):
+        """Parameters with the reference's names and shapes (comm.py:31-96); init like nn.Linear / nn.LSTMCell."""
+        H = args.hid_size
+        self.heads = nn.ModuleList([nn.Linear(H, o) for o in args.naction_heads])
+        self.encoder = nn.Linear(num_inputs, H)
+        if args.recurrent:
+            self.hidd_encoder = nn.Linear(H, H)          # allocated but unused by the reference forward (comm.py:57,125)
+            self.f_module = nn.LSTMCell(H, H)
+        elif args.share_weights:                          # comm.py:63-66: one module repeated in the list
+            self.f_module = nn.Linear(H, H)
+            self.f_modules = nn.ModuleList([self.f_module for _ in range(self.comm_passes)])
+        else:
+            self.f_modules = nn.ModuleList([nn.Linear(H, H) for _ in range(self.comm_passes)])
+        if args.share_weights:                            # comm.py:76-79
+            self.C_module = nn.Linear(H, H)
+            self.C_modules = nn.ModuleList([self.C_module for _ in range(self.comm_passes)])
+        else:
+            self.C_modules = nn.ModuleList([nn.Linear(H, H) for _ in range(self.comm_passes)])
+        if args.comm_init == 'zeros':                     # comm.py:86-88
+            for i in range(self.comm_passes):
+                self.C_modules[i].weight.data.zero_()
+        self.value_head = nn.Linear(H, 1)
+
+    def _kernel_weights(self):
+        """The tensors the kernels consume, by role (subclasses in models.py map their own parameter names here)."""
+        w = dict(enc_w=self.encoder.weight, enc_b=self.encoder.bias,
+                 c_w=[m.weight for m in self.C_modules], c_b=[m.bias for m in self.C_modules],
+                 value_w=self.value_head.weight, value_b=self.value_head.bias,
+                 head_w=[h.weight for h in self.heads], head_b=[h.bias for h in self.heads])
+        if self.recurrent:
+            w.update(w_ih=self.f_module.weight_ih, w_hh=self.f_module.weight_hh, b_ih=self.f_module.bias_ih,
+                     b_hh=self.f_module.bias_hh)
+        else:
+            w.update(f_w=[m.weight for m in self.f_modules], f_b=[m.bias for m in self.f_modules])
+        return w
+
     def __init__(self, args, num_inputs):
         super(CommNetMLP, self).__init__()
         _lib.require_cuda()
@@ -46,41 +89,40 @@ class CommNetMLP(nn.Module):
         self.continuous = args.continuous
         if self.continuous:
             raise NotImplementedError("continuous actions are outside the accelerated path")
-        if not args.recurrent or getattr(args, 'rnn_type', 'LSTM') != 'LSTM':
-            raise NotImplementedError("only the recurrent LSTM CommNet/IC3Net branch is accelerated")
-        if args.comm_passes != 1 or getattr(args, 'share_weights', False):
-            raise NotImplementedError("comm_passes != 1 / share_weights are outside the accelerated path")
+        if args.recurrent and getattr(args, 'rnn_type', 'LSTM') != 'LSTM':
+            raise NotImplementedError("recurrent CommNet needs rnn_type LSTM (main.py:151-153 forces it)")
+        if not 1 <= int(args.comm_passes) <= _lib.MAX_PASSES:
+            raise NotImplementedError("comm_passes must be in 1..%d" % _lib.MAX_PASSES)
         self.num_inputs = num_inputs
         H = args.hid_size
-        # parameters with the reference's names and shapes (comm.py:31-96); init like nn.Linear / nn.LSTMCell
-        self.heads = nn.ModuleList([nn.Linear(H, o) for o in args.naction_heads])
-        self.encoder = nn.Linear(num_inputs, H)
-        self.hidd_encoder = nn.Linear(H, H)          # allocated but unused by the reference forward (comm.py:57,125)
-        self.f_module = nn.LSTMCell(H, H)
-        self.C_modules = nn.ModuleList([nn.Linear(H, H)])
-        if args.comm_init == 'zeros':
-            self.C_modules[0].weight.data.zero_()
-        self.value_head = nn.Linear(H, 1)
+        self._build_modules(args, num_inputs)
         self.to(torch.device('cuda', torch.cuda.current_device()), torch.float32)
 
         heads = list(args.naction_heads)
         self._atot = sum(heads)
         hd = (C.c_int32 * _lib.MAX_HEADS)(*(heads + [0] * (_lib.MAX_HEADS - len(heads))))
+        var = self._variant(args)
+        self.is_variant = (var['cell'] != _lib.CELL_LSTM or var['passes'] > 1 or var['x_tanh'] or var['h_from_x'])
         self._cfg_proto = dict(N=self.nagents, H=H, O=num_inputs, nheads=len(heads), head_dim=hd,
                                hard_attn=int(bool(args.hard_attn)),
                                comm_avg=int(getattr(args, 'comm_mode', 'avg') == 'avg'),
                                comm_mask_zero=int(bool(args.comm_mask_zero)),
                                env_id0=int(getattr(args, 'env_id0', 0)),
                                seed=int(getattr(args, 'seed', 0)) & 0xFFFFFFFFFFFFFFFF,
-                               obs_off=0, obs_vocab=0, obs_ncount=0)
+                               obs_off=0, obs_vocab=0, obs_ncount=0, **var)
         self._packed = None
         self._packed_key = None
-        # 'tc' = tcgen05 tensor-core path (csrc/policy_tc.cu, hid_size 128), 'simt' = fp32 CUDA-core kernel
-        self.policy_impl = getattr(args, 'policy_impl', None) or ('tc' if H == 128 else 'simt')
+        # 'tc' = tcgen05 tensor-core path (csrc/policy_tc.cu: hid_size 128, LSTM cell, one comm pass),
+        # 'simt' = fp32 CUDA-core kernel (every variant)
+        want = getattr(args, 'policy_impl', None)
+        self.policy_impl = want or ('tc' if (H == 128 and not self.is_variant) else 'simt')
         if self.policy_impl not in ('tc', 'simt'):
             raise ValueError("policy_impl must be 'tc' or 'simt'")
         if self.policy_impl == 'tc' and H != 128:
             raise NotImplementedError("the tensor-core policy path is specialised for hid_size 128")
+        if self.policy_impl == 'tc' and self.is_variant:
+            raise NotImplementedError("the tensor-core policy path implements the recurrent LSTM policy with one comm "
+                                      "pass; this variant runs on policy_impl='simt'")
         self._ws = {}
 
     def set_obs_layout(self, off, vocab, ncount):
@@ -106,11 +148,10 @@ class CommNetMLP(nn.Module):
         return self._ws[B]
 
     def _param_list(self):
-        ps = [self.encoder.weight, self.encoder.bias, self.C_modules[0].weight, self.C_modules[0].bias,
-              self.f_module.weight_ih, self.f_module.weight_hh, self.f_module.bias_ih, self.f_module.bias_hh,
-              self.value_head.weight, self.value_head.bias]
-        for hd in self.heads:
-            ps += [hd.weight, hd.bias]
+        w = self._kernel_weights()
+        ps = []
+        for v in w.values():
+            ps += list(v) if isinstance(v, (list, tuple)) else [v]
         return ps
 
     def packed(self):
@@ -119,14 +160,19 @@ class CommNetMLP(nn.Module):
         key = tuple((p.data_ptr(), p._version) for p in ps)
         if self._packed is not None and key == self._packed_key:
             return self._packed
-        H, O = self.hid_size, self.num_inputs
-        dev = self.encoder.weight.device
+        H, O, P = self.hid_size, self.num_inputs, self.comm_passes
+        dev = ps[0].device
+        w = self._kernel_weights()
+        lstm = 'w_ih' in w
         if self._packed is None:
             nout = 1 + self._atot
             self._bufs = dict(enc_wT=torch.empty(O, H, device=dev), enc_b=torch.empty(H, device=dev),
-                              c_wT=torch.empty(H, H, device=dev), c_b=torch.empty(H, device=dev),
+                              c_wT=torch.empty(P, H, H, device=dev), c_b=torch.empty(P, H, device=dev),
                               lstm_wT=torch.empty(2 * H, 4 * H, device=dev), lstm_b=torch.empty(4 * H, device=dev),
                               head_w=torch.empty(nout, H, device=dev), head_b=torch.empty(nout, device=dev))
+            if not lstm:
+                self._bufs['f_wT'] = torch.empty(P, H, H, device=dev)
+                self._bufs['f_b'] = torch.empty(P, H, device=dev)
             if self.policy_impl == 'tc':
                 self._bufs['lstm_img'] = torch.empty(_lib.LSTM_IMG_BYTES, dtype=torch.uint8, device=dev)
                 self._bufs['bias_cat'] = torch.empty(4 * H, device=dev)
@@ -134,30 +180,50 @@ class CommNetMLP(nn.Module):
             self._packed = _lib.PolicyPacked(**{k: v.data_ptr() for k, v in self._bufs.items()})
         for p in ps:
             assert p.is_cuda and p.dtype == torch.float32 and p.is_contiguous()
-        hw = (C.c_void_p * _lib.MAX_HEADS)(*([h.weight.data_ptr() for h in self.heads] +
-                                             [None] * (_lib.MAX_HEADS - len(self.heads))))
-        hb = (C.c_void_p * _lib.MAX_HEADS)(*([h.bias.data_ptr() for h in self.heads] +
-                                             [None] * (_lib.MAX_HEADS - len(self.heads))))
-        params = _lib.PolicyParams(encoder_w=ps[0].data_ptr(), encoder_b=ps[1].data_ptr(), c_w=ps[2].data_ptr(),
-                                   c_b=ps[3].data_ptr(), w_ih=ps[4].data_ptr(), w_hh=ps[5].data_ptr(),
-                                   b_ih=ps[6].data_ptr(), b_hh=ps[7].data_ptr(), value_w=ps[8].data_ptr(),
-                                   value_b=ps[9].data_ptr(), head_w=hw, head_b=hb)
+        nh = len(w['head_w'])
+        arr = lambda lst, n: (C.c_void_p * n)(*([t.data_ptr() for t in lst] + [None] * (n - len(lst))))
+        kw = dict(encoder_w=w['enc_w'].data_ptr(), encoder_b=w['enc_b'].data_ptr(), c_w=w['c_w'][0].data_ptr(),
+                  c_b=w['c_b'][0].data_ptr(), value_w=w['value_w'].data_ptr(), value_b=w['value_b'].data_ptr(),
+                  head_w=arr(w['head_w'], _lib.MAX_HEADS), head_b=arr(w['head_b'], _lib.MAX_HEADS),
+                  c_w_pass=arr(w['c_w'], _lib.MAX_PASSES), c_b_pass=arr(w['c_b'], _lib.MAX_PASSES))
+        if lstm:
+            kw.update(w_ih=w['w_ih'].data_ptr(), w_hh=w['w_hh'].data_ptr(), b_ih=w['b_ih'].data_ptr(),
+                      b_hh=w['b_hh'].data_ptr())
+        else:
+            kw.update(f_w_pass=arr(w['f_w'], _lib.MAX_PASSES), f_b_pass=arr(w['f_b'], _lib.MAX_PASSES))
+        params = _lib.PolicyParams(**kw)
         cfg = self.policy_cfg(1)
         _lib.check(_lib.load().ic3_policy_pack(C.byref(cfg), C.byref(params), C.byref(self._packed), _lib.stream()))
         self._packed_key = key
         return self._packed
 
+    def check_errors(self):
+        """Raise if a forward() of this module set a device-side error flag (tensor-core path: pipeline watchdog, fp16
+        operand range).  One host synchronisation; the trainer checks its own flag word in collect_stat."""
+        for ws, err in self._ws.values():
+            flags = int(err.item())
+            if flags:
+                raise RuntimeError("device-side error flag %#x in CommNetMLP.forward" % flags)
+
     # ---- reference surface -------------------------------------------------------
     def forward(self, x, info={}):
-        """x = [state [B,N,O], (h, c) each [B*N, H]]; info may hold 'comm_action' and
-        'alive_mask' ([N] or [B,N]).  Returns (list of log-probs [B,N,na_k],
-        value [B*N,1], (h', c')) like comm.py:134-244."""
-        state, (h, c) = x
+        """Recurrent: x = [state [B,N,O], (h, c) each [B*N, H]] -> (list of log-probs [B,N,na_k], value [B*N,1],
+        (h', c')); non-recurrent: x = state -> (log-probs, value)  (comm.py:134-244).  info may hold 'comm_action' and
+        'alive_mask' ([N] or [B,N])."""
+        lstm = self._cfg_proto['cell'] == _lib.CELL_LSTM
+        carries = not self._cfg_proto['h_from_x']               # a hidden state enters from the previous step
+        if carries:
+            state, hid = x
+            h, c = hid if lstm else (hid, None)
+        else:
+            state, h, c = x, None, None
         B, N, H = state.shape[0], self.nagents, self.hid_size
         dev = state.device
         state = state.to(torch.float32).contiguous()
-        h = h.detach().to(dev, torch.float32).contiguous()
-        c = c.detach().to(dev, torch.float32).contiguous()
+        if h is not None:
+            h = h.detach().to(dev, torch.float32).reshape(B * N, H).contiguous()
+        if c is not None:
+            c = c.detach().to(dev, torch.float32).contiguous()
         cfg = self.policy_cfg(B)
         w = self.packed()
         lib = _lib.load()
@@ -168,17 +234,20 @@ class CommNetMLP(nn.Module):
             comm = _as_u8(info['comm_action'], B, N, dev)          # comm.py:171-175
         if 'alive_mask' in info:
             alive = _as_u8(info['alive_mask'], B, N, dev)          # comm.py:102-104
-        h2, c2 = torch.empty_like(h), torch.empty_like(c)
+        h2 = torch.empty(B * N, H, device=dev)
+        c2 = torch.empty(B * N, H, device=dev) if lstm else None
         value = torch.empty(B * N, 1, device=dev)
         logp = torch.empty(B, N, self._atot, device=dev)
         ws, err = self.workspace(B)
-        io = _lib.PolicyIO(x=xenc.data_ptr(), h=h.data_ptr(), c=c.data_ptr(), comm_action=_lib.ptr(comm),
+        io = _lib.PolicyIO(x=xenc.data_ptr(), h=_lib.ptr(h), c=_lib.ptr(c), comm_action=_lib.ptr(comm),
                            alive=_lib.ptr(alive), fresh=None, tick=None, draws=None, h_out=h2.data_ptr(),
-                           c_out=c2.data_ptr(), value=value.data_ptr(), logp=logp.data_ptr(), action=None,
+                           c_out=_lib.ptr(c2), value=value.data_ptr(), logp=logp.data_ptr(), action=None,
                            workspace=_lib.ptr(ws), err=_lib.ptr(err))
         _lib.check(lib.ic3_policy_step(C.byref(cfg), C.byref(w), C.byref(io), _lib.stream()))
         action = list(torch.split(logp, list(self.args.naction_heads), dim=-1))
-        return action, value, (h2, c2)
+        if not carries:
+            return action, value.view(B, N, 1)                     # comm.py:243-244
+        return action, value, ((h2, c2) if lstm else h2)
 
     def init_hidden(self, batch_size):
         dev = self.encoder.weight.device

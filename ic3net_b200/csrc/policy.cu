@@ -121,12 +121,19 @@ __global__ void __launch_bounds__(NT) policy_step_kernel(PolicyArgs a) {
   constexpr int H4 = H / 4;
 
   // ---- A: stage h, gates ---------------------------------------------------
+  // hidden state entering the first comm pass: the recurrent state io.h (zero at an episode start), or -- non-recurrent
+  // branch, comm.py:127-129 / models.py:24 -- the encoded observation itself
   for (int idx = tid; idx < ROWS * H4; idx += NT) {
     const int r = idx / H4, q = idx - r * H4;
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
     if (r < nrows) {
       const int e = e0 + r / N;
-      if (!(io.fresh && io.fresh[e])) v = __ldg(reinterpret_cast<const float4*>(io.h + (row0 + r) * H) + q);
+      if (cfg.h_from_x) {
+        v = __ldg(reinterpret_cast<const float4*>(io.x + (row0 + r) * H) + q);
+        if (cfg.x_tanh) v = make_float4(tanhf(v.x), tanhf(v.y), tanhf(v.z), tanhf(v.w));
+      } else if (!(io.fresh && io.fresh[e])) {
+        v = __ldg(reinterpret_cast<const float4*>(io.h + (row0 + r) * H) + q);
+      }
     }
     *reinterpret_cast<float4*>(&sm.hs[r][q * 4]) = v;
   }
@@ -152,79 +159,119 @@ __global__ void __launch_bounds__(NT) policy_step_kernel(PolicyArgs a) {
   }
   __syncthreads();
 
-  // ---- B: communication vector (comm.py:181-205) -----------------------------
-  for (int idx = tid; idx < ROWS * H4; idx += NT) {
-    const int r = idx / H4, q = idx - r * H4;
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (r < nrows && !cfg.comm_mask_zero && sm.gate[r] != 0.f) {
-      const int base = (r / N) * N;
-      for (int j = 0; j < N; ++j) {
-        if (base + j != r && sm.gate[base + j] != 0.f) {
-          const float4 hv = *reinterpret_cast<const float4*>(&sm.hs[base + j][q * 4]);
-          acc.x += hv.x; acc.y += hv.y; acc.z += hv.z; acc.w += hv.w;
+  const int npass = cfg.passes > 1 ? cfg.passes : 1;
+  for (int ps = 0; ps < npass; ++ps) {        // comm passes (comm.py:179)
+    if (ps > 0) {                             // the hidden state of the previous pass feeds this one
+      for (int idx = tid; idx < ROWS * H4; idx += NT) {
+        const int r = idx / H4, q = idx - r * H4;
+        *reinterpret_cast<float4*>(&sm.hs[r][q * 4]) = *reinterpret_cast<const float4*>(&sm.h2[r][q * 4]);
+      }
+      __syncthreads();
+    }
+    // ---- B: communication vector (comm.py:181-205) -----------------------------
+    for (int idx = tid; idx < ROWS * H4; idx += NT) {
+      const int r = idx / H4, q = idx - r * H4;
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (r < nrows && !cfg.comm_mask_zero && sm.gate[r] != 0.f) {
+        const int base = (r / N) * N;
+        for (int j = 0; j < N; ++j) {
+          if (base + j != r && sm.gate[base + j] != 0.f) {
+            const float4 hv = *reinterpret_cast<const float4*>(&sm.hs[base + j][q * 4]);
+            acc.x += hv.x; acc.y += hv.y; acc.z += hv.z; acc.w += hv.w;
+          }
+        }
+        const float d = sm.den[r];
+        acc.x /= d; acc.y /= d; acc.z /= d; acc.w /= d;
+      }
+      *reinterpret_cast<float4*>(&sm.ss[r][q * 4]) = acc;
+    }
+    __syncthreads();
+
+    // ---- C: inp = x + C_i(S) (comm.py:206,211) -----------------------------------
+    {
+      constexpr int CPT = H / 32;
+      float acc[RPT][CPT];
+#pragma unroll
+      for (int r = 0; r < RPT; ++r)
+#pragma unroll
+        for (int c = 0; c < CPT; ++c) acc[r][c] = 0.f;
+      gemm_tile<H, CPT>(sm.ss, sm.ss, H, a.w.c_wT + (size_t)ps * H * H, H, 0, sm.bs, acc);   // trailing sync: all reads of S done
+#pragma unroll
+      for (int r = 0; r < RPT; ++r) {
+        const int row = ty * RPT + r;
+#pragma unroll
+        for (int c = 0; c < CPT; ++c) {
+          const int col = tx * CPT + c;
+          float v = 0.f;
+          if (row < nrows) {
+            float xv = __ldg(io.x + (row0 + row) * H + col);
+            if (cfg.x_tanh) xv = tanhf(xv);
+            v = xv + (acc[r][c] + __ldg(a.w.c_b + (size_t)ps * H + col));
+          }
+          sm.ss[row][col] = v;
         }
       }
-      const float d = sm.den[r];
-      acc.x /= d; acc.y /= d; acc.z /= d; acc.w /= d;
     }
-    *reinterpret_cast<float4*>(&sm.ss[r][q * 4]) = acc;
-  }
-  __syncthreads();
+    __syncthreads();
 
-  // ---- C: inp = x + C(S) (comm.py:206,211) -----------------------------------
-  {
-    constexpr int CPT = H / 32;
-    float acc[RPT][CPT];
+    if (cfg.cell == IC3_CELL_TANH) {
+      // ---- D': h = tanh(x + f_i(h) + C_i(S)) (comm.py:220-224; models.py:25,84) ----------
+      constexpr int CPT = H / 32;
+      float acc[RPT][CPT];
 #pragma unroll
-    for (int r = 0; r < RPT; ++r)
+      for (int r = 0; r < RPT; ++r)
 #pragma unroll
-      for (int c = 0; c < CPT; ++c) acc[r][c] = 0.f;
-    gemm_tile<H, CPT>(sm.ss, sm.ss, H, a.w.c_wT, H, 0, sm.bs, acc);   // trailing sync: all reads of S done
+        for (int c = 0; c < CPT; ++c) acc[r][c] = 0.f;
+      gemm_tile<H, CPT>(sm.hs, sm.hs, H, a.w.f_wT + (size_t)ps * H * H, H, 0, sm.bs, acc);
 #pragma unroll
-    for (int r = 0; r < RPT; ++r) {
-      const int row = ty * RPT + r;
+      for (int r = 0; r < RPT; ++r) {
+        const int row = ty * RPT + r;
 #pragma unroll
-      for (int c = 0; c < CPT; ++c) {
-        const int col = tx * CPT + c;
-        float v = 0.f;
-        if (row < nrows) v = __ldg(io.x + (row0 + row) * H + col) + (acc[r][c] + __ldg(a.w.c_b + col));
-        sm.ss[row][col] = v;
+        for (int c = 0; c < CPT; ++c) {
+          const int col = tx * CPT + c;
+          float hn = 0.f;
+          if (row < nrows) {
+            hn = tanhf(sm.ss[row][col] + (acc[r][c] + __ldg(a.w.f_b + (size_t)ps * H + col)));
+            if (ps == npass - 1) io.h_out[(row0 + row) * H + col] = hn;
+          }
+          sm.h2[row][col] = hn;
+        }
+      }
+    } else {
+      // ---- D: LSTM cell (comm.py:213-218; torch.nn.LSTMCell, gates i,f,g,o) -------
+      for (int p = 0; p < (4 * H) / 128; ++p) {
+        float acc[RPT][4];
+#pragma unroll
+        for (int r = 0; r < RPT; ++r)
+#pragma unroll
+          for (int c = 0; c < 4; ++c) acc[r][c] = 0.f;
+        gemm_tile<H, 4>(sm.ss, sm.hs, 2 * H, a.w.lstm_wT, 4 * H, p * 128, sm.bs, acc);
+        const int u = p * 32 + tx;
+        const float4 bias = __ldg(reinterpret_cast<const float4*>(a.w.lstm_b) + u);
+#pragma unroll
+        for (int r = 0; r < RPT; ++r) {
+          const int row = ty * RPT + r;
+          float hn = 0.f;
+          if (row < nrows) {
+            const int e = e0 + row / N;
+            const bool fr = io.fresh && io.fresh[e];
+            // cell state: the recurrent input on the first pass, this thread's own c' of the previous pass afterwards
+            const float cold = ps > 0 ? io.c_out[(row0 + row) * H + u] : (fr ? 0.f : __ldg(io.c + (row0 + row) * H + u));
+            const float gi = sigmoidf_(acc[r][0] + bias.x);
+            const float gf = sigmoidf_(acc[r][1] + bias.y);
+            const float gg = tanhf(acc[r][2] + bias.z);
+            const float go = sigmoidf_(acc[r][3] + bias.w);
+            const float cn = gf * cold + gi * gg;
+            hn = go * tanhf(cn);
+            io.c_out[(row0 + row) * H + u] = cn;
+            if (ps == npass - 1) io.h_out[(row0 + row) * H + u] = hn;
+          }
+          sm.h2[row][u] = hn;
+        }
       }
     }
+    __syncthreads();
   }
-  __syncthreads();
-
-  // ---- D: LSTM cell (comm.py:213-218; torch.nn.LSTMCell, gates i,f,g,o) -------
-  for (int p = 0; p < (4 * H) / 128; ++p) {
-    float acc[RPT][4];
-#pragma unroll
-    for (int r = 0; r < RPT; ++r)
-#pragma unroll
-      for (int c = 0; c < 4; ++c) acc[r][c] = 0.f;
-    gemm_tile<H, 4>(sm.ss, sm.hs, 2 * H, a.w.lstm_wT, 4 * H, p * 128, sm.bs, acc);
-    const int u = p * 32 + tx;
-    const float4 bias = __ldg(reinterpret_cast<const float4*>(a.w.lstm_b) + u);
-#pragma unroll
-    for (int r = 0; r < RPT; ++r) {
-      const int row = ty * RPT + r;
-      float hn = 0.f;
-      if (row < nrows) {
-        const int e = e0 + row / N;
-        const bool fr = io.fresh && io.fresh[e];
-        const float cold = fr ? 0.f : __ldg(io.c + (row0 + row) * H + u);
-        const float gi = sigmoidf_(acc[r][0] + bias.x);
-        const float gf = sigmoidf_(acc[r][1] + bias.y);
-        const float gg = tanhf(acc[r][2] + bias.z);
-        const float go = sigmoidf_(acc[r][3] + bias.w);
-        const float cn = gf * cold + gi * gg;
-        hn = go * tanhf(cn);
-        io.c_out[(row0 + row) * H + u] = cn;
-        io.h_out[(row0 + row) * H + u] = hn;
-      }
-      sm.h2[row][u] = hn;
-    }
-  }
-  __syncthreads();
 
   // ---- E: heads, log-softmax, sampling (comm.py:228-239, action_utils.py:32-36) --
   const int warp = ty, lane = tx;
@@ -553,18 +600,30 @@ __global__ void pack_kernel(ic3_policy_cfg cfg, ic3_policy_params p, ic3_policy_
     const size_t j = idx / H, n = idx - j * H;
     o.enc_wT[idx] = p.encoder_w[n * O + j];
   }
-  for (size_t idx = t0; idx < (size_t)H * H; idx += stride) {   // c_wT[k][n] = W_c[n][k]
-    const size_t k = idx / H, n = idx - k * H;
-    o.c_wT[idx] = p.c_w[n * H + k];
+  const int P = cfg.passes > 1 ? cfg.passes : 1;
+  for (int ps = 0; ps < P; ++ps) {
+    const float* cw = (ps > 0 && p.c_w_pass[ps]) ? p.c_w_pass[ps] : p.c_w;
+    const float* cb = (ps > 0 && p.c_b_pass[ps]) ? p.c_b_pass[ps] : p.c_b;
+    for (size_t idx = t0; idx < (size_t)H * H; idx += stride) {   // c_wT[ps][k][n] = W_c[n][k]
+      const size_t k = idx / H, n = idx - k * H;
+      o.c_wT[(size_t)ps * H * H + idx] = cw[n * H + k];
+      if (cfg.cell == IC3_CELL_TANH) o.f_wT[(size_t)ps * H * H + idx] = p.f_w_pass[ps][n * H + k];
+    }
+    for (size_t idx = t0; idx < (size_t)H; idx += stride) {
+      if (ps > 0) o.c_b[(size_t)ps * H + idx] = cb[idx];
+      if (cfg.cell == IC3_CELL_TANH) o.f_b[(size_t)ps * H + idx] = p.f_b_pass[ps][idx];
+    }
   }
-  for (size_t idx = t0; idx < (size_t)2 * H * 4 * H; idx += stride) {  // lstm_wT[k][4u+g]
-    const size_t k = idx / (4 * H), col = idx - k * (4 * H);
-    const size_t u = col >> 2, g = col & 3;
-    o.lstm_wT[idx] = (k < (size_t)H) ? p.w_ih[(g * H + u) * H + k] : p.w_hh[(g * H + u) * H + (k - H)];
-  }
-  for (size_t idx = t0; idx < (size_t)4 * H; idx += stride) {
-    const size_t u = idx >> 2, g = idx & 3;
-    o.lstm_b[idx] = p.b_ih[g * H + u] + p.b_hh[g * H + u];
+  if (cfg.cell == IC3_CELL_LSTM) {
+    for (size_t idx = t0; idx < (size_t)2 * H * 4 * H; idx += stride) {  // lstm_wT[k][4u+g]
+      const size_t k = idx / (4 * H), col = idx - k * (4 * H);
+      const size_t u = col >> 2, g = col & 3;
+      o.lstm_wT[idx] = (k < (size_t)H) ? p.w_ih[(g * H + u) * H + k] : p.w_hh[(g * H + u) * H + (k - H)];
+    }
+    for (size_t idx = t0; idx < (size_t)4 * H; idx += stride) {
+      const size_t u = idx >> 2, g = idx & 3;
+      o.lstm_b[idx] = p.b_ih[g * H + u] + p.b_hh[g * H + u];
+    }
   }
   for (size_t idx = t0; idx < (size_t)H; idx += stride) {
     o.enc_b[idx] = p.encoder_b[idx];
@@ -595,7 +654,13 @@ int policy_check(const ic3_policy_cfg* cfg) {
     tot += cfg->head_dim[k];
   }
   if (tot > 32) return IC3_E_RANGE;  // one logit per lane
+  if (cfg->cell != IC3_CELL_LSTM && cfg->cell != IC3_CELL_TANH) return IC3_E_RANGE;
+  if (cfg->passes < 0 || cfg->passes > IC3_MAX_PASSES) return IC3_E_RANGE;
   return IC3_OK;
+}
+
+bool policy_is_variant(const ic3_policy_cfg* cfg) {
+  return cfg->cell != IC3_CELL_LSTM || cfg->passes > 1 || cfg->x_tanh || cfg->h_from_x;
 }
 
 int packed_check(const ic3_policy_packed* w) {
@@ -653,9 +718,14 @@ extern "C" int ic3_policy_pack(const ic3_policy_cfg* cfg, const ic3_policy_param
   if (!p) return IC3_E_NULL;
   rc = packed_check(out);
   if (rc) return rc;
-  if (!p->encoder_w || !p->encoder_b || !p->c_w || !p->c_b || !p->w_ih || !p->w_hh || !p->b_ih || !p->b_hh ||
-      !p->value_w || !p->value_b)
-    return IC3_E_NULL;
+  if (!p->encoder_w || !p->encoder_b || !p->c_w || !p->c_b || !p->value_w || !p->value_b) return IC3_E_NULL;
+  if (cfg->cell == IC3_CELL_LSTM && (!p->w_ih || !p->w_hh || !p->b_ih || !p->b_hh)) return IC3_E_NULL;
+  if (cfg->cell == IC3_CELL_TANH) {
+    if (!out->f_wT || !out->f_b) return IC3_E_NULL;
+    for (int i = 0; i < (cfg->passes > 1 ? cfg->passes : 1); ++i)
+      if (!p->f_w_pass[i] || !p->f_b_pass[i]) return IC3_E_NULL;
+  }
+  if (policy_is_variant(cfg) && (out->lstm_img || out->bias_cat)) return IC3_E_UNSUPPORTED;   // variants: SIMT kernel only
   for (int k = 0; k < cfg->nheads; ++k)
     if (!p->head_w[k] || !p->head_b[k]) return IC3_E_NULL;
   pack_kernel<<<296, 256, 0, (cudaStream_t)stream>>>(*cfg, *p, *out);
@@ -779,12 +849,17 @@ extern "C" int ic3_policy_step(const ic3_policy_cfg* cfg, const ic3_policy_packe
   if (rc) return rc;
   rc = packed_check(w);
   if (rc) return rc;
-  if (!io || !io->h || !io->c || !io->h_out || !io->c_out || !io->value || !io->logp) return IC3_E_NULL;
+  if (!io || !io->h_out || !io->value || !io->logp) return IC3_E_NULL;
+  if (!cfg->h_from_x && !io->h) return IC3_E_NULL;
+  if (cfg->cell == IC3_CELL_LSTM && (!io->c || !io->c_out)) return IC3_E_NULL;
   if (cfg->hard_attn && !io->comm_action) return IC3_E_NULL;
   if (cfg->N > ROWS) return IC3_E_RANGE;
-  if (io->workspace && w->lstm_img)       // tcgen05 path (policy_tc.cu); otherwise the fp32 SIMT kernel below
+  if (io->workspace && w->lstm_img) {     // tcgen05 path (policy_tc.cu); otherwise the fp32 SIMT kernel below
+    if (policy_is_variant(cfg)) return IC3_E_UNSUPPORTED;
     return ic3_tc_policy_step(cfg, w, io, (cudaStream_t)stream);
+  }
   if (!io->x) return IC3_E_NULL;
+  if (cfg->cell == IC3_CELL_TANH && (!w->f_wT || !w->f_b)) return IC3_E_NULL;
   PolicyArgs a{*cfg, *w, *io};
   IC3_DISPATCH_H(cfg->H, launch_policy<HH>(a, (cudaStream_t)stream));
 }

@@ -97,10 +97,19 @@ def derive_args(args):
         raise NotImplementedError("enemy_comm is outside the accelerated path")
     if args.plot or args.display:
         raise NotImplementedError("--plot / --display (visdom, curses) are outside the accelerated path")
-    if not args.commnet or args.random:
-        raise NotImplementedError("only the CommNet / IC3Net policies (comm.py) are accelerated; "
-                                  "models.py baselines are outside the path")
     return args
+
+
+def make_policy(args, num_inputs):
+    """main.py:162-169."""
+    from . import models
+    if args.commnet:
+        return CommNetMLP(args, num_inputs)
+    if args.random:
+        return models.Random(args, num_inputs)
+    if args.recurrent:
+        return models.RNN(args, num_inputs)
+    return models.MLP(args, num_inputs)
 
 
 LOG_FIELDS = (('epoch', None), ('reward', 'num_episodes'), ('enemy_reward', 'num_episodes'),
@@ -226,7 +235,7 @@ def main(argv=None):
         print(args)
 
     args.record_for_grad = not args.rollout_only     # keep the inputs compute_grad re-runs (trainer.py)
-    policy_net = CommNetMLP(args, num_inputs)
+    policy_net = make_policy(args, num_inputs)
     # MultiGPUTrainer broadcasts rank 0's parameters: replicas are identical whatever the ranks' RNG state was
     trainer = MultiGPUTrainer(args, lambda: Trainer(args, policy_net, env))
 

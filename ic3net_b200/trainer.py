@@ -43,8 +43,45 @@ RolloutBatch = namedtuple('RolloutBatch', ('action', 'logp', 'value', 'reward', 
                                            'episode_mini_mask', 'alive_mask', 'valid'))
 
 
+def policy_forward_torch(net, x, h, c, g, n_alive):
+    """Differentiable torch restatement of the policy step the kernels run (comm.py:134-244 for every variant of
+    ic3_policy_cfg.cell / passes / x_tanh / h_from_x), on the module's own parameters.  x: encoder output [R, H];
+    h, c: [R, H] entering the step; g: comm gate per agent [B, N] (alive * comm_action); n_alive: [B, 1].
+    Returns (h', c', value [R, 1], [log-probs per head [R, na]])."""
+    w, cp = net._kernel_weights(), net._cfg_proto
+    B, N = g.shape
+    H = x.shape[1]
+    lstm = cp['cell'] == _lib.CELL_LSTM
+    if cp['x_tanh']:
+        x = torch.tanh(x)                                                              # comm.py:127-128
+    hid = x if cp['h_from_x'] else h                                                   # comm.py:129
+    den = torch.where(n_alive > 1, n_alive - 1, torch.ones_like(n_alive)) if cp['comm_avg'] else torch.ones_like(n_alive)
+    gg = g.unsqueeze(-1)
+    for ps in range(max(1, cp['passes'])):                                             # comm.py:179
+        if cp['comm_mask_zero'] or N < 2:
+            S = torch.zeros_like(hid)
+        else:
+            hv = hid.view(B, N, H)
+            tot = (gg * hv).sum(1, keepdim=True)
+            S = (gg * (tot - gg * hv) / den.unsqueeze(-1)).reshape(B * N, H)           # comm.py:181-205
+        cvec = F.linear(S, w['c_w'][ps], w['c_b'][ps])                                 # comm.py:206
+        if lstm:
+            gates = F.linear(x + cvec, w['w_ih'], w['b_ih']) + F.linear(hid, w['w_hh'], w['b_hh'])   # comm.py:211-218
+            gi, gf, gq, go = gates.chunk(4, dim=1)
+            c = torch.sigmoid(gf) * c + torch.sigmoid(gi) * torch.tanh(gq)
+            hid = torch.sigmoid(go) * torch.tanh(c)
+        else:
+            hid = torch.tanh(x + F.linear(hid, w['f_w'][ps], w['f_b'][ps]) + cvec)     # comm.py:220-224
+    value = F.linear(hid, w['value_w'], w['value_b'])                                  # comm.py:228
+    logps = [F.log_softmax(F.linear(hid, hw, hb), dim=-1) for hw, hb in zip(w['head_w'], w['head_b'])]
+    return hid, c, value, logps
+
+
 class Trainer(object):
     def __init__(self, args, policy_net, env):
+        if not hasattr(policy_net, 'packed'):
+            raise NotImplementedError("Trainer drives policies that run on the CUDA kernels (CommNetMLP, models.MLP, "
+                                      "models.RNN); models.Random has no kernel path")
         self.args = args
         self.policy_net = policy_net
         self.env = env                       # GymWrapper
@@ -408,8 +445,8 @@ class Trainer(object):
         b, net, args = self._buf, self.policy_net, self.args
         B, N, H = self.env.env.nenvs, args.nagents, args.hid_size
         hard = bool(args.hard_attn) and bool(args.commnet)
-        comm_avg = getattr(args, 'comm_mode', 'avg') == 'avg'
-        w_e, b_e = net.encoder.weight, net.encoder.bias
+        w = net._kernel_weights()
+        w_e, b_e = w['enc_w'], w['enc_b']
         w_eT = None if self.is_tj else w_e.t().contiguous()
         loss = torch.zeros((), device=h.device)
         st = dict(action_loss=torch.zeros((), device=h.device), value_loss=torch.zeros((), device=h.device),
@@ -428,25 +465,15 @@ class Trainer(object):
             g = alive
             if hard:
                 g = g * torch.where(fresh, torch.zeros_like(b['s_comm'][t]), b['s_comm'][t]).float()  # :171-175
-            if args.comm_mask_zero:
-                S = torch.zeros_like(h)
-            else:
-                hv = h.view(B, N, H)
-                gg = g.unsqueeze(-1)
-                tot = (gg * hv).sum(1, keepdim=True)
-                den = torch.where(n_alive > 1, n_alive - 1, torch.ones_like(n_alive)) if comm_avg \
-                    else torch.ones_like(n_alive)
-                S = (gg * (tot - gg * hv) / den.unsqueeze(-1)).reshape(B * N, H)           # comm.py:181-205
-            inp = x + net.C_modules[0](S)                                                  # comm.py:206,211
-            h, c = net.f_module(inp, (h, c))                                               # comm.py:213-218
-            value = net.value_head(h).view(B, N)
+            h, c, value, logps = policy_forward_torch(net, x, h, c, g, n_alive)
+            value = value.view(B, N)
             alive_post = b['ralive'][t].float()
             act = b['action'][t].long()
             lp_taken = torch.zeros(B, N, device=h.device)
             ent = torch.zeros((), device=h.device)
             vmask = b['valid'][t].float().view(B, 1, 1)            # 0 for slots that already completed their batch
-            for k, head in enumerate(net.heads):
-                lp = F.log_softmax(head(h), dim=-1).view(B, N, -1)                         # comm.py:239
+            for k, lp in enumerate(logps):
+                lp = lp.view(B, N, -1)                                                     # comm.py:239
                 lp_taken = lp_taken + lp.gather(-1, act[..., k:k + 1]).squeeze(-1)         # utils.py:42-46
                 ent = ent - (lp * lp.exp() * vmask).sum()
             a_loss = (-adv[t] * lp_taken * alive_post).sum()                               # trainer.py:198-201
@@ -570,20 +597,28 @@ class Trainer(object):
         return st['losses']
 
     def _param_structs(self):
-        """ic3_policy_params of the parameters and of their gradient buffers (reference layouts)."""
+        """ic3_policy_params of the parameters and of their gradient buffers (reference layouts), by kernel role."""
         net = self.policy_net
-        ps = net._param_list()
-        for p in ps:
-            if p.grad is None:
-                p.grad = torch.zeros_like(p)
+        w = net._kernel_weights()
+        scratch = self.__dict__.setdefault('_grad_scratch', {})
+
+        def grad_ptr(p):
+            if isinstance(p, torch.nn.Parameter):
+                if p.grad is None:
+                    p.grad = torch.zeros_like(p)
+                return p.grad.data_ptr()
+            key = p.data_ptr()                       # frozen buffer (models.py: zero comm projection): discard its gradient
+            if key not in scratch:
+                scratch[key] = torch.zeros_like(p)
+            return scratch[key].data_ptr()
 
         def mk(get):
-            hw = (C.c_void_p * _lib.MAX_HEADS)(*([get(h.weight) for h in net.heads] + [None] * (_lib.MAX_HEADS - len(net.heads))))
-            hb = (C.c_void_p * _lib.MAX_HEADS)(*([get(h.bias) for h in net.heads] + [None] * (_lib.MAX_HEADS - len(net.heads))))
-            return _lib.PolicyParams(encoder_w=get(ps[0]), encoder_b=get(ps[1]), c_w=get(ps[2]), c_b=get(ps[3]),
-                                     w_ih=get(ps[4]), w_hh=get(ps[5]), b_ih=get(ps[6]), b_hh=get(ps[7]),
-                                     value_w=get(ps[8]), value_b=get(ps[9]), head_w=hw, head_b=hb)
-        return mk(lambda p: p.data_ptr()), mk(lambda p: p.grad.data_ptr())
+            arr = lambda lst: (C.c_void_p * _lib.MAX_HEADS)(*([get(t) for t in lst] + [None] * (_lib.MAX_HEADS - len(lst))))
+            return _lib.PolicyParams(encoder_w=get(w['enc_w']), encoder_b=get(w['enc_b']), c_w=get(w['c_w'][0]),
+                                     c_b=get(w['c_b'][0]), w_ih=get(w['w_ih']), w_hh=get(w['w_hh']), b_ih=get(w['b_ih']),
+                                     b_hh=get(w['b_hh']), value_w=get(w['value_w']), value_b=get(w['value_b']),
+                                     head_w=arr(w['head_w']), head_b=arr(w['head_b']))
+        return mk(lambda p: p.data_ptr()), mk(grad_ptr)
 
     def _compute_grad_manual(self, adv, ret, W, nw):
         """``args.grad_impl == 'manual'``: the same gradient from the explicit backward formulas of bptt.py (no autograd
@@ -591,6 +626,8 @@ class Trainer(object):
         measured on the GPU."""
         from . import bptt
         b, net, args = self._buf, self.policy_net, self.args
+        if getattr(net, 'is_variant', False) or type(net).__name__ != 'CommNetMLP':
+            raise NotImplementedError("grad_impl='manual' covers the recurrent LSTM CommNet / IC3Net with one comm pass")
         B, N = self.env.env.nenvs, args.nagents
         T = b['T']
         P, G = {}, {}

@@ -202,8 +202,21 @@ typedef struct {
    * so that the class part can come from a per-position table (ic3_*_encoder_table) and all forms stay
    * bit-identical.  predator_prey: (0, D*D+4, 2); traffic_junction: (2, vocab, 1).  obs_vocab = 0: one sum. */
   int32_t obs_off, obs_vocab, obs_ncount;
+  /* Policy variants of comm.py / models.py (all zero = the recurrent LSTM CommNet / IC3Net with one comm pass):
+   *   cell      IC3_CELL_LSTM: (h, c) = LSTMCell(x + C_i(S), (h, c))                       (comm.py:213-218)
+   *             IC3_CELL_TANH: h = tanh(x + f_i(h) + C_i(S))                               (comm.py:220-224; models.py:25,
+   *                            84 with comm_mask_zero: the MLP / RNN baselines)
+   *   passes    comm passes per forward, 1..IC3_MAX_PASSES (comm.py:179), weights C_i / f_i per pass (share_weights:
+   *             the same pointers)
+   *   x_tanh    x = tanh(encoder(obs)) (non-recurrent branch, comm.py:127-128; models.py:24)
+   *   h_from_x  the hidden state entering the first pass is x itself instead of io->h (comm.py:129)
+   * Variants run on the fp32 SIMT kernel (the tcgen05 path implements the all-zero configuration). */
+  int32_t cell, passes, x_tanh, h_from_x;
   int32_t reserved0;
 } ic3_policy_cfg;
+
+enum { IC3_CELL_LSTM = 0, IC3_CELL_TANH = 1 };
+#define IC3_MAX_PASSES 4
 
 /* Parameters in the reference state_dict layout (device, fp32). */
 typedef struct {
@@ -219,6 +232,11 @@ typedef struct {
   const float* value_b;    /* [1] */
   const float* head_w[IC3_MAX_HEADS]; /* heads.k.weight [na_k, H] */
   const float* head_b[IC3_MAX_HEADS]; /* [na_k] */
+  /* variants (ic3_policy_cfg.cell / passes); all NULL for the default configuration */
+  const float* c_w_pass[IC3_MAX_PASSES]; /* C_modules.i.weight [H, H] for pass i >= 1 (index 0 unused: c_w) */
+  const float* c_b_pass[IC3_MAX_PASSES];
+  const float* f_w_pass[IC3_MAX_PASSES]; /* IC3_CELL_TANH: f_modules.i.weight [H, H], every pass */
+  const float* f_b_pass[IC3_MAX_PASSES];
 } ic3_policy_params;
 
 /* Kernel-side layout, produced once per weight update by ic3_policy_pack. */
@@ -239,6 +257,10 @@ typedef struct {
    * bias_cat: [4H] b_ih + b_hh + W_ih.c_b, column 4*u+gate. */
   void* lstm_img;
   float* bias_cat;
+  /* variants: c_wT / c_b hold `passes` consecutive [H, H] / [H] blocks; IC3_CELL_TANH: f_wT [passes][H, H]
+   * (f_wT[i][k][n] = f_i.weight[n][k]) and f_b [passes][H]; NULL otherwise */
+  float* f_wT;
+  float* f_b;
   int32_t* flags;  /* device word written by ic3_policy_pack (IC3_ERR_FP16_RANGE when a folded weight does not fit the
                       operand split), OR-ed into ic3_policy_io.err by every policy step; may be NULL */
 } ic3_policy_packed;

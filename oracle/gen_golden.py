@@ -606,6 +606,105 @@ def gen_log_case(name="log_contract"):
         json.dump(out, f, indent=0)
 
 
+def gen_variant_case(name, seed, obs_dim, heads, model, nrep=4, use_alive=False, **kw):
+    """Forward fixtures of the policy variants from the UNMODIFIED reference modules: CommNetMLP with
+    comm_passes > 1 / share_weights / the non-recurrent tanh branch, and models.MLP / models.RNN.  The module's own
+    (seeded) initial state_dict is stored with the inputs and outputs; the numpy restatement
+    oracle.policy.forward_variant is asserted equal on the way."""
+    import torch
+    torch.set_default_dtype(torch.float64)
+    ref_shims.install()
+    import comm as ref_comm
+    import models as ref_models
+    args = ref_shims.make_args(**kw)
+    args.naction_heads, args.continuous = list(heads), False
+    args.num_actions, args.dim_actions = list(heads), len(heads)
+    torch.manual_seed(seed)
+    if model == "commnet":
+        if args.recurrent:
+            args.rnn_type = "LSTM"
+        net = ref_comm.CommNetMLP(args, obs_dim)
+    elif model == "mlp":
+        net = ref_models.MLP(args, obs_dim)
+    else:
+        net = ref_models.RNN(args, obs_dim)
+    sd = {k: v.detach().numpy().copy() for k, v in net.state_dict().items()}
+    params = policy.params_to_f64(sd)
+    n, H = args.nagents, args.hid_size
+    lstm = (model == "commnet" and args.recurrent) or (model == "rnn" and args.rnn_type == "LSTM")
+    carries = (model == "rnn") or (model == "commnet" and args.recurrent)
+    passes = args.comm_passes if model == "commnet" else 1
+    roles = policy.roles_of(params, "commnet" if model == "commnet" else model, bool(args.recurrent), passes)
+    variant = dict(passes=passes, x_tanh=(model == "mlp") or (model == "commnet" and not args.recurrent),
+                   h_from_x=(model == "mlp") or (model == "commnet" and not args.recurrent))
+    hard = bool(args.hard_attn) and model == "commnet"
+    rs = np.random.RandomState(seed + 1)
+    out = dict(obs=[], h=[], c=[], comm=[], alive=[], value=[], h2=[], c2=[])
+    for k in range(len(heads)):
+        out["logp%d" % k] = []
+    for rep in range(nrep):
+        obs = np.zeros((n, obs_dim))
+        nz = rs.randint(0, obs_dim, size=(n, min(8, obs_dim)))
+        for i in range(n):
+            obs[i, nz[i]] = rs.randint(1, 4, size=nz.shape[1])
+        h = rs.uniform(-1, 1, size=(n, H)) if rep else np.zeros((n, H))
+        c = rs.uniform(-2, 2, size=(n, H)) if rep else np.zeros((n, H))
+        comm = rs.randint(0, 2, size=n) if rep != 1 else np.zeros(n, dtype=np.int64)
+        alive = rs.randint(0, 2, size=n).astype(np.float64) if (use_alive and model == "commnet") else None
+        info = {}
+        if hard:
+            info["comm_action"] = comm
+        if alive is not None:
+            info["alive_mask"] = alive.copy()
+        tobs = torch.from_numpy(obs[None])
+        with torch.no_grad():
+            if not carries:
+                act, val = net(tobs, info)
+                h2 = c2 = None
+            elif lstm:
+                act, val, (h2, c2) = net([tobs, (torch.from_numpy(h), torch.from_numpy(c))], info)
+            else:
+                act, val, h2 = net([tobs, torch.from_numpy(h[None])], info)
+                c2 = None
+        lo, ov, oh2, oc2 = policy.forward_variant(roles, obs, h if carries else None, c if lstm else None,
+                                                  comm if hard else None, alive, hard, args.comm_mode,
+                                                  bool(args.comm_mask_zero) or model != "commnet", **variant)
+        assert np.allclose(val.numpy().reshape(-1), ov, rtol=1e-12, atol=1e-13), name
+        for k in range(len(heads)):
+            assert np.allclose(act[k].numpy().reshape(n, -1), lo[k], rtol=1e-12, atol=1e-13), name
+            out["logp%d" % k].append(lo[k])
+        if h2 is not None:
+            assert np.allclose(h2.numpy().reshape(n, H), oh2, rtol=1e-12, atol=1e-13), name
+        if c2 is not None:
+            assert np.allclose(c2.numpy(), oc2, rtol=1e-12, atol=1e-13), name
+        out["obs"].append(obs); out["h"].append(h); out["c"].append(c); out["comm"].append(comm)
+        out["alive"].append(np.ones(n) if alive is None else alive)
+        out["value"].append(ov); out["h2"].append(oh2); out["c2"].append(oc2 if oc2 is not None else np.zeros((n, H)))
+    meta = dict(kind="variant", model=model, obs_dim=obs_dim, heads=list(heads), use_alive=bool(alive is not None),
+                hard_attn=hard, lstm=bool(lstm), carries=bool(carries),
+                args={k: v for k, v in vars(args).items() if isinstance(v, (int, float, str, bool))})
+    arrays = {k: np.array(v) for k, v in out.items()}
+    for k, v in sd.items():
+        arrays["sd_" + k] = v
+    save(name, meta, **arrays)
+
+
+def gen_variant_cases():
+    gen_variant_case("var_commnet_passes2", 91, 45, (5, 2), "commnet", nagents=5, hid_size=128, ic3net=True,
+                     comm_passes=2, use_alive=True)
+    gen_variant_case("var_commnet_share3", 92, 45, (5,), "commnet", nagents=4, hid_size=64, commnet=True,
+                     comm_passes=3, share_weights=True)
+    gen_variant_case("var_commnet_nonrec2", 93, 61, (2, 2), "commnet", nagents=6, hid_size=128, ic3net=True,
+                     recurrent=False, comm_passes=2, use_alive=True)
+    gen_variant_case("var_commnet_nonrec_share", 94, 29, (5,), "commnet", nagents=3, hid_size=32, commnet=True,
+                     recurrent=False, comm_passes=2, share_weights=True, comm_mode="sum")
+    gen_variant_case("var_mlp", 95, 29, (5,), "mlp", nagents=3, hid_size=128, commnet=False, recurrent=False)
+    gen_variant_case("var_rnn_tanh", 96, 29, (5,), "rnn", nagents=3, hid_size=128, commnet=False, recurrent=True,
+                     rnn_type="MLP")
+    gen_variant_case("var_rnn_lstm", 97, 61, (2,), "rnn", nagents=5, hid_size=128, commnet=False, recurrent=True,
+                     rnn_type="LSTM")
+
+
 def gen_hid128_grad_cases():
     """Gradient fixtures at hid_size 128 (the shape the tensor-core rollout and the BPTT kernels run at) covering the
     loss / comm variants: entropy bonus, normalised advantages, cooperative returns, comm_mode sum, plain CommNet (no
@@ -622,6 +721,11 @@ def gen_hid128_grad_cases():
 
 
 def main():
+    if "--variants-only" in sys.argv:
+        import warnings
+        warnings.filterwarnings("ignore")
+        gen_variant_cases()
+        return 0
     if "--grad128-only" in sys.argv:
         import warnings
         warnings.filterwarnings("ignore")
@@ -694,6 +798,7 @@ def main():
                   max_steps=20, hid_size=64, commnet=True, difficulty="easy", add_rate_min=0.3, add_rate_max=0.3,
                   batch_size=50, mean_ratio=0.5, gamma=0.9)
     gen_hid128_grad_cases()
+    gen_variant_cases()
     gen_rmsprop_case("rmsprop_ref", 81)
     gen_log_case()
     return 0

@@ -90,6 +90,63 @@ def forward(params, obs, h, c, comm_action=None, alive=None, hard_attn=True,
     return logps, value, h2, c2, x
 
 
+def roles_of(params, model="commnet", recurrent=True, passes=1):
+    """Parameter arrays by kernel role for the reference's model families (comm.py:31-96, models.py:8-96)."""
+    p = params
+    heads = [(p["heads.%d.weight" % k], p["heads.%d.bias" % k]) for k in range(nheads(p))]
+    r = dict(value=(p["value_head.weight"], p["value_head.bias"]), heads=heads)
+    if model == "commnet":
+        r["enc"] = (p["encoder.weight"], p["encoder.bias"])
+        r["C"] = [(p["C_modules.%d.weight" % i], p["C_modules.%d.bias" % i]) for i in range(passes)]
+        if recurrent:
+            r["lstm"] = tuple(p["f_module." + k] for k in ("weight_ih", "weight_hh", "bias_ih", "bias_hh"))
+        else:
+            r["f"] = [(p["f_modules.%d.weight" % i], p["f_modules.%d.bias" % i]) for i in range(passes)]
+    else:                                   # models.MLP / models.RNN: independent controllers, no comm
+        H = p["value_head.weight"].shape[1]
+        r["enc"] = (p["affine1.weight"], p["affine1.bias"])
+        r["C"] = [(np.zeros((H, H)), np.zeros(H))]
+        if "lstm_unit.weight_ih" in p:
+            r["lstm"] = tuple(p["lstm_unit." + k] for k in ("weight_ih", "weight_hh", "bias_ih", "bias_hh"))
+        else:
+            r["f"] = [(p["affine2.weight"], p["affine2.bias"])]
+    return r
+
+
+def forward_variant(roles, obs, h, c, comm_action=None, alive=None, hard_attn=False, comm_mode="avg",
+                    comm_mask_zero=False, passes=1, x_tanh=False, h_from_x=False):
+    """Policy step of every variant (comm.py:134-244; models.py:22-25,68-85) for ONE environment:
+      x = encoder(obs) [tanh'd in the non-recurrent branch]; hidden = x or the recurrent state;
+      per pass: S = gated mean of hidden, c_i = C_i(S); LSTM: (h, c) = LSTMCell(x + c_i, (h, c));
+      tanh cell: h = tanh(x + f_i(h) + c_i).   Returns (logps, value [N], h' [N,H], c' or None)."""
+    obs = np.asarray(obs, dtype=np.float64)
+    x = obs @ roles["enc"][0].T + roles["enc"][1]
+    if x_tanh:
+        x = np.tanh(x)
+    hid = x if h_from_x else np.asarray(h, dtype=np.float64)
+    n, H = hid.shape
+    alive_v = np.ones(n) if alive is None else np.asarray(alive, dtype=np.float64)
+    n_alive = alive_v.sum()
+    g = alive_v.copy()
+    if hard_attn:
+        g = g * np.asarray(comm_action, dtype=np.float64)
+    c2 = None if c is None else np.asarray(c, dtype=np.float64)
+    for i in range(passes):
+        S = comm_sum(hid, g, n_alive, comm_mode, comm_mask_zero)
+        cvec = S @ roles["C"][i][0].T + roles["C"][i][1]
+        if "lstm" in roles:
+            w_ih, w_hh, b_ih, b_hh = roles["lstm"]
+            gates = (x + cvec) @ w_ih.T + b_ih + hid @ w_hh.T + b_hh
+            gi, gf, gg, go = (gates[:, k * H:(k + 1) * H] for k in range(4))
+            c2 = _sigmoid(gf) * c2 + _sigmoid(gi) * np.tanh(gg)
+            hid = _sigmoid(go) * np.tanh(c2)
+        else:
+            hid = np.tanh(x + hid @ roles["f"][i][0].T + roles["f"][i][1] + cvec)
+    value = (hid @ roles["value"][0].T + roles["value"][1])[:, 0]
+    logps = [_log_softmax(hid @ w.T + b) for w, b in roles["heads"]]
+    return logps, value, hid, c2
+
+
 def sample_from_logp(logp_row, u):
     """Inverse CDF: smallest a with sum_{i<=a} exp(logp_i) > u, else the last index.
 
