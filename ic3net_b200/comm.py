@@ -96,7 +96,8 @@ class CommNetMLP(nn.Module):
         self.num_inputs = num_inputs
         H = args.hid_size
         self._build_modules(args, num_inputs)
-        self.to(torch.device('cuda', torch.cuda.current_device()), torch.float32)
+        self._dev = torch.device('cuda', torch.cuda.current_device())
+        self.to(self._dev, torch.float32)
 
         heads = list(args.naction_heads)
         self._atot = sum(heads)
@@ -142,7 +143,7 @@ class CommNetMLP(nn.Module):
         if B not in self._ws:
             cfg = self.policy_cfg(B)
             nbytes = int(_lib.load().ic3_policy_workspace_bytes(C.byref(cfg)))
-            dev = self.encoder.weight.device
+            dev = self._dev
             self._ws[B] = (torch.empty(nbytes, dtype=torch.uint8, device=dev),
                            torch.zeros(1, dtype=torch.int32, device=dev))
         return self._ws[B]
@@ -250,6 +251,6 @@ class CommNetMLP(nn.Module):
         return action, value, ((h2, c2) if lstm else h2)
 
     def init_hidden(self, batch_size):
-        dev = self.encoder.weight.device
+        dev = self._dev
         return tuple((torch.zeros(batch_size * self.nagents, self.hid_size, device=dev),
                       torch.zeros(batch_size * self.nagents, self.hid_size, device=dev)))

@@ -535,7 +535,9 @@ class Trainer(object):
             if dh is not None:                     # gradient arriving from the later window
                 loss = loss + (h1 * dh).sum() + (c1 * dc).sum()
             loss.backward()
-            dh, dc = h0.grad.detach(), c0.grad.detach()
+            # variants without a cell state / without a carried hidden state leave these gradients undefined: zero
+            dh = h0.grad.detach() if h0.grad is not None else torch.zeros_like(h0)
+            dc = c0.grad.detach() if c0.grad is not None else torch.zeros_like(c0)
             tot += torch.stack([st[key] for key in self.LOSS_KEYS]).double()
         return tot
 

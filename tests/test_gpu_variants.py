@@ -128,6 +128,8 @@ def test_variant_trains_and_recompute_agrees_with_the_kernels(model, extra):
                 g = g * torch.where(fresh, torch.zeros_like(b["s_comm"][t]), b["s_comm"][t]).float()
             h, c, value, logps = policy_forward_torch(net, x, h, c, g, alive.sum(1, keepdim=True))
             v = (b["valid"][t] != 0)
+            if not bool(v.any()):
+                continue
             got_v = b["value"][t].view(B, N)[v]
             worst = max(worst, float((got_v - value.view(B, N)[v]).abs().max()))
             lp = torch.cat(logps, -1).view(B, N, -1)[v]
