@@ -510,11 +510,11 @@ __device__ __forceinline__ void lstm_cell4(const uint32_t (&v)[16], const float 
 //                      overlaps the MMAs of item i+1
 // Work item = (128-row tile, 256-column half); item 2t and 2t+1 share the A tile (second read hits L2).
 constexpr int NSTAGE_P = 4;
-constexpr int HEAD_PAD = 8;          // outputs (value + action logits) the fused epilogue supports
+constexpr int HEAD_PAD = IC3_HEAD_PAD;   // outputs (value + action logits) the fused epilogue supports
 constexpr int EPI_WARPS = 16;        // 4 warps per TMEM lane quarter, 64 accumulator columns (16 hidden units) each
 constexpr int EPI_THREADS = EPI_WARPS * 32;
 constexpr int TC_P_THREADS = EPI_THREADS + 64;   // + producer warp + MMA warp
-constexpr int NSLOT = 8;             // partial-logit slots per row: (column half of the item) x (column quarter of the warp)
+constexpr int NSLOT = IC3_HEAD_NSLOT;   // partial-logit slots per row: (column half of the item) x (column quarter of the warp)
 
 // Two adjacent lanes (rows 2k, 2k+1 of the tile) hold 8 consecutive floats of their own row each (a = first 4,
 // b = last 4).  Written directly, every STG.128 of the warp touches 32 half-used 32-byte sectors; after one
@@ -1050,62 +1050,14 @@ __global__ void __launch_bounds__(128) heads_finish_kernel(ic3_policy_cfg cfg, i
   ic3_pdl_wait();      // the partial logits come from the LSTM kernel
   const long row = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (row >= (long)cfg.B * cfg.N) return;
-  float logit[HEAD_PAD];
-  const float4* p4 = reinterpret_cast<const float4*>(partial + (size_t)row * NSLOT * HEAD_PAD);
-  {
-    float4 a = p4[0], b = p4[1];
+  HeadsFinish f;
+  f.partial = partial; f.head_b = w.head_b; f.nheads = cfg.nheads;
 #pragma unroll
-    for (int sl = 1; sl < NSLOT; ++sl) {
-      const float4 c = p4[2 * sl], d = p4[2 * sl + 1];
-      a.x += c.x; a.y += c.y; a.z += c.z; a.w += c.w;
-      b.x += d.x; b.y += d.y; b.z += d.z; b.w += d.w;
-    }
-    logit[0] = a.x; logit[1] = a.y; logit[2] = a.z; logit[3] = a.w;
-    logit[4] = b.x; logit[5] = b.y; logit[6] = b.z; logit[7] = b.w;
-  }
-  int atot = 0;
-  for (int k = 0; k < cfg.nheads; ++k) atot += cfg.head_dim[k];
-#pragma unroll
-  for (int o = 0; o < HEAD_PAD; ++o) logit[o] += (o < 1 + atot) ? __ldg(w.head_b + o) : 0.f;
-  io.value[row] = logit[0];
+  for (int k = 0; k < IC3_MAX_HEADS; ++k) f.head_dim[k] = cfg.head_dim[k];
+  f.seed = cfg.seed; f.env_id0 = cfg.env_id0; f.tick = io.tick; f.draws = io.draws;
+  f.value = io.value; f.logp = io.logp; f.action = io.action;
   const int e = (int)(row / cfg.N), i = (int)(row - (long)e * cfg.N);
-  const bool do_sample = io.action != nullptr;
-  uint4 d24 = make_uint4(0, 0, 0, 0);
-  if (do_sample && !io.draws)
-    d24 = ic3_draw24(cfg.seed, cfg.env_id0 + (uint32_t)e, io.tick ? io.tick[e] : 0u, IC3_STREAM_ACTION, (uint32_t)i);
-  int off = 1;
-  for (int k = 0; k < cfg.nheads; ++k) {
-    const int na = cfg.head_dim[k];
-    float m = -INFINITY;
-#pragma unroll
-    for (int o = 1; o < HEAD_PAD; ++o)
-      if (o >= off && o < off + na) m = fmaxf(m, logit[o]);
-    float ssum = 0.f;
-#pragma unroll
-    for (int o = 1; o < HEAD_PAD; ++o)
-      if (o >= off && o < off + na) ssum += expf(logit[o] - m);
-    const float lse = m + logf(ssum);
-    uint32_t u24 = 0;
-    if (do_sample) u24 = io.draws ? io.draws[(size_t)row * cfg.nheads + k] : ic3_word(d24, k);
-    const float u = (float)u24 * 5.9604644775390625e-08f;
-    float cdf = 0.f;
-    int act = na - 1;
-    bool found = false;
-#pragma unroll
-    for (int o = 1; o < HEAD_PAD; ++o) {
-      if (o >= off && o < off + na) {
-        const float lp = logit[o] - lse;
-        io.logp[(size_t)row * atot + (o - 1)] = lp;
-        cdf += expf(lp);
-        if (!found && cdf > u) {
-          act = o - off;
-          found = true;
-        }
-      }
-    }
-    if (do_sample) io.action[(size_t)row * cfg.nheads + k] = act;
-    off += na;
-  }
+  heads_finish_row(f, row, e, i, nullptr);
 }
 
 }  // namespace

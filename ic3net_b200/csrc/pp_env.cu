@@ -137,7 +137,10 @@ __global__ void pp_step_kernel(PPArgs a, const int32_t* __restrict__ act, int ac
       if (a.st.done[e]) {  // :129-130 RuntimeError("Episode is done")
         if (lane == 0) atomicOr(err, IC3_ERR_EPISODE_DONE);
       } else {
-        const int av = lane < N ? act[((size_t)e * N + lane) * act_stride] : 4;
+        int av = 4;
+        if (r.has && r.io.head_partial) av = ic3_rollout_heads(r.io, a.cfg.seed, a.cfg.env_id0, a.st.tick, e, N, lane);
+        else if (lane < N) av = act[((size_t)e * N + lane) * act_stride];
+        if (lane >= N) av = 4;
         if (lane < N && (av < 0 || av > a.cfg.naction)) atomicOr(err, IC3_ERR_BAD_ACTION);  // :137 (sic, <=)
         if (lane < N && !rch) {  // _take_action :212-252: every move is a clamped move
           if (av == 0) rr = max(0, rr - 1);
@@ -185,6 +188,15 @@ __global__ void pp_step_kernel(PPArgs a, const int32_t* __restrict__ act, int ac
             }
           }
         }
+      }
+    }
+    if (do_step && r.has && r.io.snap_T > 0) {          // inputs of the next policy step, for compute_grad
+      __syncwarp();
+      ic3_rollout_snapshot(r.io, e, a.cfg.B, N, lane);
+      if (r.io.snap_pp_loc && r.io.t + 1 < r.io.snap_T && lane <= N) {
+        int* d = r.io.snap_pp_loc + (((size_t)(r.io.t + 1) * a.cfg.B + e) * (N + 1) + lane) * 2;
+        d[0] = rr;
+        d[1] = cc;
       }
     }
     if (lane <= N) {

@@ -116,7 +116,10 @@ __global__ void tj_step_kernel(TJArgs a, const int32_t* __restrict__ act, int ac
     } else if (do_step) {
       // ---- _take_action :540-581 ----
       int completed = 0;
-      const int av = lane < N ? act[i * act_stride] : 1;
+      int av = 1;
+      if (r.has && r.io.head_partial) av = ic3_rollout_heads(r.io, cfg.seed, cfg.env_id0, a.st.tick, e, N, lane);
+      else if (lane < N) av = act[i * act_stride];
+      if (lane >= N) av = 1;
       if (lane < N && (av < 0 || av > 2)) atomicOr(err, IC3_ERR_BAD_ACTION);  // :228 (sic, <=)
       if (lane < N && alive) {
         wait += 1;                       // :546
@@ -210,6 +213,20 @@ __global__ void tj_step_kernel(TJArgs a, const int32_t* __restrict__ act, int ac
           rr = cc = alive = wait = lact = 0;
           rid = rpos = -1;
         }
+      }
+    }
+    if (do_step && r.has && r.io.snap_T > 0) {          // inputs of the next policy step, for compute_grad
+      __syncwarp();
+      ic3_rollout_snapshot(r.io, e, cfg.B, N, lane);
+      if (r.io.t + 1 < r.io.snap_T && lane < N) {
+        const size_t k = ((size_t)(r.io.t + 1) * cfg.B + e) * N + lane;
+        if (r.io.snap_tj_loc) {
+          r.io.snap_tj_loc[2 * k] = rr;
+          r.io.snap_tj_loc[2 * k + 1] = cc;
+        }
+        if (r.io.snap_tj_alive) r.io.snap_tj_alive[k] = (uint8_t)alive;
+        if (r.io.snap_tj_last_act) r.io.snap_tj_last_act[k] = (uint8_t)lact;
+        if (r.io.snap_tj_route_id) r.io.snap_tj_route_id[k] = rid;
       }
     }
     if (lane < N) {

@@ -246,19 +246,38 @@ class Trainer(object):
             src = dict(tj_env=C.addressof(e.cfg), tj_state=C.addressof(e.state)) if self.is_tj else \
                 dict(pp_env=C.addressof(e.cfg), pp_state=C.addressof(e.state))
             src['x_table'] = _lib.ptr(self._encoder_table(cfg, w))
+        # tensor-core path with <= 7 action logits: the env step kernel finishes the policy heads (value, log-softmax,
+        # sampling) from the LSTM epilogue's partial logits -- one launch less per lock-step iteration
+        fuse_heads = (net.policy_impl == 'tc' and 1 + sum(args.naction_heads) <= 8 and ws is not None
+                      and bool(getattr(args, 'fuse_heads', True)))
+        heads_kw = {}
+        if fuse_heads:
+            hd = (C.c_int32 * _lib.MAX_HEADS)(*(list(args.naction_heads) + [0] * (_lib.MAX_HEADS - nh)))
+            heads_kw = dict(head_partial=lib.ic3_policy_partial_ptr(C.byref(cfg), ws.data_ptr()),
+                            head_b=net._bufs['head_b'].data_ptr(), head_dim=hd)
+        snap = {}
+        if rec:
+            snap = dict(snap_T=T, snap_fresh=b['s_fresh'].data_ptr(), snap_comm=b['s_comm'].data_ptr(),
+                        snap_alive=b['s_alive'].data_ptr(), snap_tep=b['s_tep'].data_ptr())
+            if not self.is_tj:
+                snap['snap_pp_loc'] = b['s_loc'].data_ptr()
+            elif gk:
+                snap.update(snap_tj_loc=b['s_tjloc'].data_ptr(), snap_tj_alive=b['s_tjalive'].data_ptr(),
+                            snap_tj_last_act=b['s_tjlast'].data_ptr(), snap_tj_route_id=b['s_tjroute'].data_ptr())
         for t in range(T):
             if rec:
-                b['s_fresh'][t].copy_(b['fresh'])
-                b['s_comm'][t].copy_(b['comm'])
-                b['s_alive'][t].copy_(b['alive'])
-                b['s_tep'][t].copy_(b['t_ep'])
-                if not self.is_tj:
-                    b['s_loc'][t].copy_(e.loc)
-                elif gk:
-                    b['s_tjloc'][t].copy_(e.car_loc)
-                    b['s_tjalive'][t].copy_(e.alive_mask)
-                    b['s_tjlast'][t].copy_(e.car_last_act)
-                    b['s_tjroute'][t].copy_(e.route_id)
+                if t == 0:          # inputs of the first step; the env step kernels record those of every later step
+                    b['s_fresh'][0].copy_(b['fresh'])
+                    b['s_comm'][0].copy_(b['comm'])
+                    b['s_alive'][0].copy_(b['alive'])
+                    b['s_tep'][0].copy_(b['t_ep'])
+                    if not self.is_tj:
+                        b['s_loc'][0].copy_(e.loc)
+                    elif gk:
+                        b['s_tjloc'][0].copy_(e.car_loc)
+                        b['s_tjalive'][0].copy_(e.alive_mask)
+                        b['s_tjlast'][0].copy_(e.car_last_act)
+                        b['s_tjroute'][0].copy_(e.route_id)
                 if not gk and t % self.grad_window == 0:
                     b['ck_h'][t // self.grad_window].copy_(b['h'])
                     b['ck_c'][t // self.grad_window].copy_(b['c'])
@@ -287,12 +306,14 @@ class Trainer(object):
                                fresh=b['fresh'].data_ptr(), tick=e.tick.data_ptr(), draws=None,
                                h_out=hout.data_ptr(), c_out=cout.data_ptr(), value=b['value'][t].data_ptr(),
                                logp=b['logp'][t].data_ptr(), action=b['action'][t].data_ptr(),
-                               workspace=_lib.ptr(ws), err=b['err'].data_ptr(), **src)
+                               workspace=_lib.ptr(ws), err=b['err'].data_ptr(), defer_heads=int(fuse_heads), **src)
             _lib.check(lib.ic3_policy_step(C.byref(cfg), C.byref(w), C.byref(io), s))
+            if fuse_heads:
+                heads_kw.update(head_value=b['value'][t].data_ptr(), head_logp=b['logp'][t].data_ptr())
             r = _lib.RolloutIO(t=t, max_steps=args.max_steps, nheads=nh, hard_attn=hard,
                                comm_action_one=int(bool(args.comm_action_one)),
                                last=int(t == T - 1 and quota <= 0), batch_size=int(quota),
-                               halted=b['halted'].data_ptr(), rec_valid=b['valid'].data_ptr(),
+                               halted=b['halted'].data_ptr(), rec_valid=b['valid'].data_ptr(), **snap, **heads_kw,
                                action=b['action'][t].data_ptr(), t_ep=b['t_ep'].data_ptr(),
                                fresh=b['fresh'].data_ptr(), comm_next=b['comm'].data_ptr(),
                                alive_next=b['alive'].data_ptr(), rec_reward=b['reward'].data_ptr(),

@@ -119,6 +119,29 @@ typedef struct {
   int32_t reserved0;
   uint8_t* halted;         /* [B] in/out: slot has completed its batch */
   uint8_t* rec_valid;      /* [T, B] 1 = a real step of this slot, 0 = slot already halted (may be NULL) */
+  /* Inputs of the NEXT policy step, recorded for Trainer.compute_grad (all optional; written at index t + 1 when
+   * t + 1 < snap_T; index 0 is the caller's): what the policy will see as fresh / comm_action / alive_mask / step
+   * index, and the environment state its observation is taken from. */
+  int32_t snap_T;
+  int32_t reserved1;
+  uint8_t* snap_fresh;     /* [T, B] */
+  uint8_t* snap_comm;      /* [T, B, N] */
+  uint8_t* snap_alive;     /* [T, B, N] */
+  int32_t* snap_tep;       /* [T, B] */
+  int32_t* snap_pp_loc;    /* [T, B, N+1, 2]   predator_prey */
+  int32_t* snap_tj_loc;    /* [T, B, N, 2]     traffic_junction ... */
+  uint8_t* snap_tj_alive;  /* [T, B, N] */
+  uint8_t* snap_tj_last_act; /* [T, B, N] */
+  int32_t* snap_tj_route_id; /* [T, B, N] */
+  /* Fused policy heads (tcgen05 path, ic3_policy_io.defer_heads): when head_partial != NULL the env step kernel first
+   * finishes the heads of this step from the LSTM epilogue's partial logits -- value, log-softmax, inverse-CDF sampling
+   * on the action stream of (cfg.seed, cfg.env_id0 + env, tick) -- writing head_value / head_logp and the `action`
+   * tensor (which is then an OUTPUT of the step, not an input), and consumes head 0 itself.  One launch less per step. */
+  const float* head_partial; /* ic3_policy_partial_ptr(...) */
+  const float* head_b;       /* ic3_policy_packed.head_b */
+  float* head_value;         /* [B*N] */
+  float* head_logp;          /* [B*N, sum(na)] */
+  int32_t head_dim[IC3_MAX_HEADS];
 } ic3_rollout_io;
 
 /* reset(): predator_prey_env.py:146-168.  Draws N+1 distinct cells per env from
@@ -313,7 +336,14 @@ typedef struct {
   /* optional, fused index encoder only: [positions, H] table of ic3_pp_encoder_table / ic3_tj_encoder_table
    * for the CURRENT weights (device pointer); needs cfg->obs_vocab > 0. */
   const float* x_table;
+  /* tcgen05 path with at most 7 action logits: 1 = stop after the LSTM kernel and leave the heads' partial logits in
+   * the workspace (ic3_policy_partial_ptr); the env step kernel finishes them (ic3_rollout_io.head_partial). */
+  int32_t defer_heads;
+  int32_t reserved0;
 } ic3_policy_io;
+
+/* Partial-logit block inside a tcgen05 workspace (NULL when the configuration does not use it). */
+const float* ic3_policy_partial_ptr(const ic3_policy_cfg* cfg, const void* workspace);
 
 /* Scratch the tcgen05 policy path needs for a batch of cfg->B environments (0 when unsupported). */
 uint64_t ic3_policy_workspace_bytes(const ic3_policy_cfg* cfg);
