@@ -111,8 +111,11 @@ def test_cli_runs_reference_flags(capsys):
                    "2", "--batch_size", "40", "--seed", "4", "--detach_gap", "10", "--lrate", "0.001"])
     out = capsys.readouterr().out
     assert rc == 0 and "Epoch 2" in out and "steps/s" in out
-    with pytest.raises(NotImplementedError):
-        cli.main(["--env_name", "predator_prey", "--nagents", "3", "--dim", "5", "--nenvs", "4"])   # MLP baseline
+    # the independent-controller baselines of models.py (main.py:162-169): MLP, and RNN with --recurrent (IC / IRIC)
+    small = ["--env_name", "predator_prey", "--nagents", "3", "--dim", "5", "--max_steps", "10", "--nenvs", "4",
+             "--hid_size", "64", "--num_epochs", "1", "--epoch_size", "1", "--batch_size", "10", "--seed", "2"]
+    assert cli.main(small) == 0
+    assert cli.main(small + ["--recurrent", "--mean_ratio", "0"]) == 0
     rc = cli.main(["--env_name", "traffic_junction", "--nagents", "5", "--dim", "6", "--vision", "0", "--max_steps",
                    "20", "--hid_size", "128", "--ic3net", "--recurrent", "--nenvs", "32", "--num_epochs", "1",
                    "--epoch_size", "1", "--batch_size", "20", "--seed", "4", "--difficulty", "easy", "--add_rate_min",
