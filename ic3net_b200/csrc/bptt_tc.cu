@@ -266,8 +266,6 @@ __device__ __forceinline__ uint4 pack8_hi_lo(const float (&x)[8], float scale, u
   return make_uint4(h[0], h[1], h[2], h[3]);
 }
 
-__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
-
 __global__ void __launch_bounds__(TC_P_THREADS, 1) bptt_gates_kernel(GatesArgs g, const __half* __restrict__ a_img,
                                                                     const __half* __restrict__ b_img,
                                                                     const float* __restrict__ bias_cat, int nitems,
@@ -275,14 +273,12 @@ __global__ void __launch_bounds__(TC_P_THREADS, 1) bptt_gates_kernel(GatesArgs g
   extern __shared__ __align__(1024) unsigned char smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + NSTAGE_P * STAGE_BYTES);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
-  int* s_prog = reinterpret_cast<int*>(bars + 18);
   float* s_hw = reinterpret_cast<float*>(smem + NSTAGE_P * STAGE_BYTES + 256);   // head weights, unit-major [128][8]
   float* s_bias = s_hw + TC_H * HEAD_PAD;
   const uint32_t bar_full = smem_u32(bars), bar_empty = smem_u32(bars + NSTAGE_P);
   const uint32_t bar_tfull = smem_u32(bars + 2 * NSTAGE_P), bar_tempty = smem_u32(bars + 2 * NSTAGE_P + 2);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
-    *s_prog = 0;
     for (int s = 0; s < NSTAGE_P; ++s) {
       mbar_init(bar_full + 8 * s, 1);
       mbar_init(bar_empty + 8 * s, 1);
@@ -309,30 +305,12 @@ __global__ void __launch_bounds__(TC_P_THREADS, 1) bptt_gates_kernel(GatesArgs g
   const uint32_t tmem_base = *tmem_slot;
   const int ncta = gridDim.x;
 
-  if (warp == EPI_WARPS && lane != 0) {
-    // ===== L2 prefetch of the epilogue's operands (c_{t-1}, dh, dc: 64 hidden units x 128 rows each) one work item
-    // ahead: the epilogue cannot keep a whole item's loads in registers, so its per-group loads must hit L2 =====
-    int li = 0;
-    for (int item = blockIdx.x; item < nitems; item += ncta, ++li) {
-      // throttle: item li is prefetched once the operand producer has started item li - 1 (never more than ~2 items =
-      // 200 KB per SM ahead of the epilogue, or the prefetches would evict each other from L2)
-      while (*reinterpret_cast<volatile int*>(s_prog) < li) __nanosleep(200);
-      const int tile = item >> 1, nh = item & 1;
-      for (int idx = lane - 1; idx < TC_M * 2 * 3; idx += 31) {          // (row, 128-byte half of the 64 units, array)
-        const int r = idx / 6, rem = idx - r * 6, half = rem & 1, arr = rem >> 1;
-        const int row = tile * TC_M + r;
-        if (row >= g.R) continue;
-        const float* base = arr == 0 ? g.c_prev : (arr == 1 ? g.dh : g.dc);
-        prefetch_l2(base + (size_t)row * TC_H + nh * 64 + half * 32);
-      }
-    }
-  } else if (warp == EPI_WARPS && lane == 0) {
+  if (warp == EPI_WARPS && lane == 0) {
     // ===== producer (as lstm_tc_kernel) =====
     uint32_t li = 0;
     bool ok = true;
     const uint32_t smem_base = smem_u32(smem);
     for (int item = blockIdx.x; item < nitems && ok; item += ncta, ++li) {
-      *reinterpret_cast<volatile int*>(s_prog) = (int)li + 1;       // progress of the operand stream (prefetch throttle)
       const int tile = item >> 1, nh = item & 1;
       const unsigned char* a_src = reinterpret_cast<const unsigned char*>(a_img) + (size_t)tile * TC_NCHUNK * A_CHUNK_BYTES;
       const unsigned char* b_src = reinterpret_cast<const unsigned char*>(b_img) + (size_t)nh * TC_NCHUNK * B_CHUNK_BYTES;
@@ -349,7 +327,6 @@ __global__ void __launch_bounds__(TC_P_THREADS, 1) bptt_gates_kernel(GatesArgs g
         bulk_g2s(dst + A_CHUNK_BYTES, b_src + (size_t)c * B_CHUNK_BYTES, B_CHUNK_BYTES, bar_full + 8 * s);
       }
     }
-    *reinterpret_cast<volatile int*>(s_prog) = 1 << 30;             // release the prefetch lanes on any exit path
   } else if (warp == EPI_WARPS + 1 && lane == 0) {
     // ===== MMA issuer (as lstm_tc_kernel) =====
     const uint32_t idesc = (1u << 4) | ((uint32_t)(TC_NH >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
