@@ -387,7 +387,16 @@ def gpu_arm(opts):
     if "e2e" not in skip:
         if world > 1:
             dist.barrier()
-        mine = e2e_loop(a, env, net, min(max(K, 50), 200), np, torch, select_action)
+        # the framework's public API hands observations over as HANDLES on the env state (args.obs_api = 'handle',
+        # ic3net_b200/lazy_obs.py: env.step returns a LazyObs, CommNetMLP.forward evaluates the encoder from the state,
+        # bit-identical x); the dense-tensor form of the same API is timed beside it
+        ah, envh, neth, trh = build(opts.obs_mode, obs_api="handle")
+        mine = e2e_loop(ah, envh, neth, min(max(K, 50), 200), np, torch, select_action)
+        mine["obs_api"] = "handle"
+        del trh
+        dense_e2e = e2e_loop(a, env, net, min(max(K, 50), 100), np, torch, select_action)
+        mine["dense_obs_api"] = dict(value=dense_e2e["value"], ms_per_step=dense_e2e["ms_per_step"],
+                                     note="same loop with env.step returning the dense [B,N,O] tensor (per rank)")
         if world > 1:
             agg = torch.tensor([mine["seconds"], float(mine["steps"])], device=dev, dtype=torch.float64)
             mx = agg.clone()
@@ -687,7 +696,7 @@ def e2e_loop(a, env, net, steps, np, torch, select_action):
         if not is_tj and bool(done_h.any()):                             # finished PP envs start a new episode
             m = done_h.to(torch.uint8)
             e.reset(mask=m, want_obs=False)
-            obs = env._flatten_obs(e._get_obs())
+            obs = env._flatten_obs(e._obs_handle() if e.obs_api == 'handle' else e._get_obs())
             keep = (~done_h).to(obs.device).repeat_interleave(N).unsqueeze(1).float()
             hc = (hc[0] * keep, hc[1] * keep)
             if a.hard_attn:
@@ -723,7 +732,8 @@ def e2e_loop(a, env, net, steps, np, torch, select_action):
                 step_ms_sorted_tail=[round(1e3 * x, 3) for x in per_step[-4:]],
                 cuda_mallocs_in_loop=int(ms1.get("num_device_alloc", 0) - ms0.get("num_device_alloc", 0)),
                 cuda_frees_in_loop=int(ms1.get("num_device_free", 0) - ms0.get("num_device_free", 0)),
-                api="CommNetMLP.forward -> select_action -> host actions -> GymWrapper.step -> host reward/done")
+                api="GymWrapper.reset/step (observation %s) -> CommNetMLP.forward -> select_action -> host actions -> "
+                    "GymWrapper.step -> host reward/done" % ("handle" if e.obs_api == "handle" else "tensor"))
 
 
 def main():

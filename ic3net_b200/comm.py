@@ -19,6 +19,7 @@ import torch
 from torch import nn
 
 from . import _lib
+from .lazy_obs import LazyObs
 
 
 def _as_u8(v, B, N, device):
@@ -125,6 +126,7 @@ class CommNetMLP(nn.Module):
             raise NotImplementedError("the tensor-core policy path implements the recurrent LSTM policy with one comm "
                                       "pass; this variant runs on policy_impl='simt'")
         self._ws = {}
+        self._xtab, self._xtab_key = None, None     # per-position encoder table of forward() on observation handles
 
     def set_obs_layout(self, off, vocab, ncount):
         """Observation layout hint (include/ic3net_b200.h, ic3_policy_cfg.obs_vocab): lets the encoder sum the
@@ -220,16 +222,22 @@ class CommNetMLP(nn.Module):
             state, h, c = x, None, None
         B, N, H = state.shape[0], self.nagents, self.hid_size
         dev = state.device
-        state = state.to(torch.float32).contiguous()
+        lazy = isinstance(state, LazyObs)            # observation handle (lazy_obs.py): encoder from the env state
+        if not lazy:
+            state = state.to(torch.float32).contiguous()
         if h is not None:
             h = h.detach().to(dev, torch.float32).reshape(B * N, H).contiguous()
         if c is not None:
             c = c.detach().to(dev, torch.float32).contiguous()
-        cfg = self.policy_cfg(B)
-        w = self.packed()
         lib = _lib.load()
-        xenc = torch.empty(B * N, H, device=dev)
-        _lib.check(lib.ic3_encoder_dense(C.byref(cfg), C.byref(w), state.data_ptr(), xenc.data_ptr(), _lib.stream()))
+        src, xenc = {}, None
+        if lazy:
+            cfg, w, src, xenc = self._index_encoder(state, B)
+        else:
+            cfg = self.policy_cfg(B)
+            w = self.packed()
+            xenc = torch.empty(B * N, H, device=dev)
+            _lib.check(lib.ic3_encoder_dense(C.byref(cfg), C.byref(w), state.data_ptr(), xenc.data_ptr(), _lib.stream()))
         comm = alive = None
         if self.args.hard_attn:
             comm = _as_u8(info['comm_action'], B, N, dev)          # comm.py:171-175
@@ -240,15 +248,45 @@ class CommNetMLP(nn.Module):
         value = torch.empty(B * N, 1, device=dev)
         logp = torch.empty(B, N, self._atot, device=dev)
         ws, err = self.workspace(B)
-        io = _lib.PolicyIO(x=xenc.data_ptr(), h=_lib.ptr(h), c=_lib.ptr(c), comm_action=_lib.ptr(comm),
+        io = _lib.PolicyIO(x=_lib.ptr(xenc), h=_lib.ptr(h), c=_lib.ptr(c), comm_action=_lib.ptr(comm),
                            alive=_lib.ptr(alive), fresh=None, tick=None, draws=None, h_out=h2.data_ptr(),
                            c_out=_lib.ptr(c2), value=value.data_ptr(), logp=logp.data_ptr(), action=None,
-                           workspace=_lib.ptr(ws), err=_lib.ptr(err))
+                           workspace=_lib.ptr(ws), err=_lib.ptr(err), **src)
         _lib.check(lib.ic3_policy_step(C.byref(cfg), C.byref(w), C.byref(io), _lib.stream()))
         action = list(torch.split(logp, list(self.args.naction_heads), dim=-1))
         if not carries:
             return action, value.view(B, N, 1)                     # comm.py:243-244
         return action, value, ((h2, c2) if lstm else h2)
+
+    def _index_encoder(self, obs, B):
+        """Encoder input for an observation HANDLE: returns (cfg, packed weights, PolicyIO source fields, x tensor or
+        None).  Tensor-core path with a small vision window: the encoder is fused into the policy step (x is formed from
+        the env state and the per-position table inside the operand-preparation kernel); otherwise the index-form
+        encoder kernel writes x.  Either way the same sums in the same order as ic3_encoder_dense."""
+        e = obs.check_current()
+        lib = _lib.load()
+        is_tj = type(e).__name__ == 'TrafficJunctionEnv'
+        if self._cfg_proto['obs_vocab'] == 0 and getattr(e, 'obs_layout', (0, 0, 0))[1]:
+            self.set_obs_layout(*e.obs_layout)
+        cfg = self.policy_cfg(B)
+        cfg.seed, cfg.env_id0 = e.cfg.seed, e.cfg.env_id0
+        w = self.packed()
+        W = 2 * e.vision + 1
+        if self.policy_impl == 'tc' and W * W <= 25 and cfg.obs_vocab > 0:
+            if self._xtab is None:
+                self._xtab = torch.empty(e.obs_positions, self.hid_size, device=self._dev)
+            if self._xtab_key != self._packed_key:
+                fn = lib.ic3_tj_encoder_table if is_tj else lib.ic3_pp_encoder_table
+                _lib.check(fn(C.byref(e.cfg), C.byref(cfg), C.byref(w), self._xtab.data_ptr(), _lib.stream()))
+                self._xtab_key = self._packed_key
+            src = dict(tj_env=C.addressof(e.cfg), tj_state=C.addressof(e.state)) if is_tj else \
+                dict(pp_env=C.addressof(e.cfg), pp_state=C.addressof(e.state))
+            src['x_table'] = self._xtab.data_ptr()
+            return cfg, w, src, None
+        xenc = torch.empty(B * self.nagents, self.hid_size, device=self._dev)
+        fn = lib.ic3_tj_encoder_index if is_tj else lib.ic3_pp_encoder_index
+        _lib.check(fn(C.byref(e.cfg), C.byref(e.state), C.byref(cfg), C.byref(w), xenc.data_ptr(), _lib.stream()))
+        return cfg, w, {}, xenc
 
     def init_hidden(self, batch_size):
         dev = self._dev

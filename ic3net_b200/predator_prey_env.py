@@ -25,6 +25,8 @@ class PredatorPreyEnv(object):
         self.POS_PREY_REWARD = 0.05
         self.episode_over = False
         self.strict = True      # raise "Episode is done" eagerly (one 4-byte host read per step)
+        self.obs_version = 0    # bumped by every step / reset: validity of LazyObs handles (lazy_obs.py)
+        self.obs_api = 'dense'  # 'handle': reset / step return a LazyObs instead of the dense tensor (args.obs_api)
 
     def init_args(self, parser):
         env = parser.add_argument_group('Prey Predator task')
@@ -42,6 +44,9 @@ class PredatorPreyEnv(object):
 
     def multi_agent_init(self, args):
         _lib.require_cuda()
+        self.obs_api = getattr(args, 'obs_api', 'dense')
+        if self.obs_api not in ('dense', 'handle'):
+            raise ValueError("obs_api must be 'dense' or 'handle'")
         for key in ('dim', 'vision', 'moving_prey', 'mode', 'enemy_comm'):
             setattr(self, key, getattr(args, key))
         self.nprey = args.nenemies
@@ -110,6 +115,10 @@ class PredatorPreyEnv(object):
     def _new_obs(self):
         return torch.empty(self.obs_shape, dtype=torch.float32, device=self.device)
 
+    def _obs_handle(self):
+        from .lazy_obs import LazyObs
+        return LazyObs(self)
+
     def set_state(self, predator_loc, prey_loc):
         """Inject spawn positions (parity tests / replays) instead of sampling them."""
         loc = torch.as_tensor(np.concatenate([np.asarray(predator_loc).reshape(self.nenvs, self.npredator, 2),
@@ -123,12 +132,14 @@ class PredatorPreyEnv(object):
 
     def reset(self, mask=None, want_obs=True):
         self.episode_over = False
-        obs = self._new_obs() if want_obs else None
+        self.obs_version += 1
+        lazy = want_obs and self.obs_api == 'handle'
+        obs = self._new_obs() if (want_obs and not lazy) else None
         m = None if mask is None else torch.as_tensor(mask).to(self.device, torch.uint8).contiguous()
         _lib.check(_lib.load().ic3_pp_reset(C.byref(self.cfg), C.byref(self.state), _lib.ptr(m), _lib.ptr(obs),
                                             _lib.stream()))
         self.stat = dict()
-        return obs
+        return self._obs_handle() if lazy else obs
 
     def _get_obs(self):
         obs = self._new_obs()
@@ -152,10 +163,14 @@ class PredatorPreyEnv(object):
     def step(self, action, obs_out=None):
         act = self._as_action(action)
         reward = torch.empty(self.nenvs, self.npredator, dtype=torch.float32, device=self.device)
-        obs = self._new_obs() if obs_out is None else obs_out
+        lazy = obs_out is None and self.obs_api == 'handle'
+        obs = None if lazy else (self._new_obs() if obs_out is None else obs_out)
+        self.obs_version += 1
         _lib.check(_lib.load().ic3_pp_step(C.byref(self.cfg), C.byref(self.state), act.data_ptr(), 1,
-                                           reward.data_ptr(), obs.data_ptr(), self.err.data_ptr(), None,
+                                           reward.data_ptr(), _lib.ptr(obs), self.err.data_ptr(), None,
                                            _lib.stream()))
+        if lazy:
+            obs = self._obs_handle()
         if self.strict:
             self.check_errors()
         done = self.done.bool()

@@ -27,6 +27,8 @@ class TrafficJunctionEnv(object):
         self.CRASH_PENALTY = -10
         self.episode_over = False
         self.strict = True
+        self.obs_version = 0    # bumped by every step / reset: validity of LazyObs handles (lazy_obs.py)
+        self.obs_api = 'dense'  # 'handle': reset / step return a LazyObs instead of the dense tensor (args.obs_api)
 
     def init_args(self, parser):
         env = parser.add_argument_group('Traffic Junction task')
@@ -44,6 +46,9 @@ class TrafficJunctionEnv(object):
 
     def multi_agent_init(self, args):
         _lib.require_cuda()
+        self.obs_api = getattr(args, 'obs_api', 'dense')
+        if self.obs_api not in ('dense', 'handle'):
+            raise ValueError("obs_api must be 'dense' or 'handle'")
         for key in ('dim', 'vision', 'add_rate_min', 'add_rate_max', 'curr_start', 'curr_end', 'difficulty',
                     'vocab_type'):
             setattr(self, key, getattr(args, key))
@@ -120,6 +125,10 @@ class TrafficJunctionEnv(object):
     def _new_obs(self):
         return torch.empty(self.obs_shape, dtype=torch.float32, device=self.device)
 
+    def _obs_handle(self):
+        from .lazy_obs import LazyObs
+        return LazyObs(self)
+
     def reset(self, epoch=None, mask=None, want_obs=True):
         self.episode_over = False
         self.stat = dict()
@@ -128,11 +137,13 @@ class TrafficJunctionEnv(object):
         if epoch is not None and epoch_range > 0 and add_rate_range > 0 and epoch > self.epoch_last_update:
             self.curriculum(epoch)
             self.epoch_last_update = epoch
-        obs = self._new_obs() if want_obs else None
+        self.obs_version += 1
+        lazy = want_obs and self.obs_api == 'handle'
+        obs = self._new_obs() if (want_obs and not lazy) else None
         m = None if mask is None else torch.as_tensor(mask).to(self.device, torch.uint8).contiguous()
         _lib.check(_lib.load().ic3_tj_reset(C.byref(self.cfg), C.byref(self.state), _lib.ptr(m), _lib.ptr(obs),
                                             _lib.stream()))
-        return obs
+        return self._obs_handle() if lazy else obs
 
     def curriculum(self, epoch):
         step_size = 0.01
@@ -165,10 +176,14 @@ class TrafficJunctionEnv(object):
             d = torch.as_tensor(np.asarray(draws, dtype=np.int64)).to(self.device, torch.int32).contiguous()
             assert d.numel() == self.nenvs * self.cfg.G * 3
         reward = torch.empty(self.nenvs, self.ncar, dtype=torch.float32, device=self.device)
-        obs = self._new_obs() if obs_out is None else obs_out
+        lazy = obs_out is None and self.obs_api == 'handle'
+        obs = None if lazy else (self._new_obs() if obs_out is None else obs_out)
+        self.obs_version += 1
         _lib.check(_lib.load().ic3_tj_step(C.byref(self.cfg), C.byref(self.state), act.data_ptr(), 1, _lib.ptr(d),
-                                           reward.data_ptr(), obs.data_ptr(), self.err.data_ptr(), None,
+                                           reward.data_ptr(), _lib.ptr(obs), self.err.data_ptr(), None,
                                            _lib.stream()))
+        if lazy:
+            obs = self._obs_handle()
         if self.strict:
             self.check_errors()
         debug = {'car_loc': self.car_loc, 'alive_mask': self.alive_mask.clone(), 'wait': self.wait,

@@ -245,3 +245,49 @@ def test_heads_finished_by_the_env_step_kernel_equal_the_separate_kernel(name):
         res.append((cpu(b.action).copy(), cpu(b.value).copy(), cpu(b.logp).copy(), cpu(b.reward).copy()))
     for x, y in zip(res[0], res[1]):
         assert np.array_equal(x, y)
+
+
+@pytest.mark.parametrize("name,impl", [("ep_pp_hard_ic3net", "tc"), ("ep_tj_medium_ic3net", "tc"), ("ep_pp_easy_ic3net", "simt"),
+                                       ("ep_tj_medium_v1_commnet", "simt")])
+def test_observation_handle_api_is_bit_identical_to_the_dense_tensor_api(name, impl):
+    """args.obs_api = 'handle': GymWrapper.reset/step return a LazyObs (ic3net_b200/lazy_obs.py) and CommNetMLP.forward
+    evaluates the encoder from the env state; the same public-API loop with dense observation tensors must give the same
+    values, log-probs, hidden states and rewards bit for bit, and the handle must materialise the exact dense tensor."""
+    from ic3net_b200.action_utils import select_action
+    from ic3net_b200.lazy_obs import LazyObs
+    meta, z = load_golden(name)
+    out = {}
+    for api in ("dense", "handle"):
+        args, env, net, tr, p = build(meta, 9, "index", seed=77, impl=impl, obs_api=api)
+        B, N = 9, args.nagents
+        obs = env.reset(0)
+        assert isinstance(obs, LazyObs) == (api == "handle")
+        hc = net.init_hidden(B)
+        info = {"comm_action": torch.zeros(B, N, dtype=torch.uint8, device="cuda")} if args.hard_attn else {}
+        rec = []
+        for t in range(6):
+            if api == "handle" and t == 2:
+                dense_now = obs.dense().clone()
+            action_out, value, hc = net([obs, hc], info)
+            action = select_action(args, action_out)
+            obs, reward, done, info_env = env.step([action[..., 0]])
+            info = {}
+            if args.hard_attn:
+                info["comm_action"] = action[..., -1].to(torch.uint8) if not args.comm_action_one else torch.ones(
+                    B, N, dtype=torch.uint8, device="cuda")
+            if "alive_mask" in info_env:
+                info["alive_mask"] = info_env["alive_mask"]
+            rec.append((cpu(value).copy(), cpu(torch.cat(action_out, -1)).copy(), cpu(hc[0]).copy(), cpu(reward).copy(),
+                        cpu(action).copy()))
+            if api == "dense" and t == 1:
+                out["dense_obs_t2"] = cpu(obs).copy()
+        if api == "handle":
+            assert np.array_equal(cpu(dense_now), out["dense_obs_t2"])          # the handle materialises the same tensor
+            with pytest.raises(RuntimeError, match="stale"):
+                stale = env.reset(0)
+                env.step([action[..., 0]])
+                stale.dense()
+        out[api] = rec
+    for a, b in zip(out["dense"], out["handle"]):
+        for x, y in zip(a, b):
+            assert np.array_equal(x, y)
