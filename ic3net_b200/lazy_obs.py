@@ -16,10 +16,10 @@ import torch
 
 
 class LazyObs(object):
-    def __init__(self, env):
+    def __init__(self, env, shape=None):
         self.env = env
         self.version = env.obs_version
-        self.shape = tuple(env.obs_shape)
+        self.shape = tuple(env.obs_shape) if shape is None else tuple(shape)
         self.device = env.device
         self.dtype = torch.float32
 
@@ -32,7 +32,7 @@ class LazyObs(object):
 
     # ---- tensor-like surface: materialise on demand ----------------------------------------------------
     def dense(self):
-        return self.check_current()._get_obs()
+        return self.check_current()._get_obs().reshape(self.shape)
 
     def size(self, dim=None):
         return self.shape if dim is None else self.shape[dim]
@@ -40,19 +40,28 @@ class LazyObs(object):
     def dim(self):
         return len(self.shape)
 
-    def reshape(self, *shape):
-        shape = tuple(shape[0]) if len(shape) == 1 and isinstance(shape[0], (tuple, list)) else tuple(shape)
-        known = [s for s in shape if s != -1]
-        numel = 1
+    def numel(self):
+        n = 1
         for s in self.shape:
-            numel *= s
+            n *= s
+        return n
+
+    def reshape(self, *shape):
+        """A reshaped handle (still lazy): GymWrapper._flatten_obs turns [nenvs, N, W, W, V] into [nenvs, N, obs_dim]."""
+        shape = tuple(shape[0]) if len(shape) == 1 and isinstance(shape[0], (tuple, list)) else tuple(shape)
         prod = 1
-        for s in known:
-            prod *= s
-        full = tuple(s if s != -1 else numel // max(1, prod) for s in shape)
-        if full == self.shape:
-            return self                                   # GymWrapper._flatten_obs: already [nenvs, N, obs_dim]
-        return self.dense().reshape(*shape)
+        for s in shape:
+            if s != -1:
+                prod *= s
+        full = tuple(s if s != -1 else self.numel() // max(1, prod) for s in shape)
+        n = 1
+        for s in full:
+            n *= s
+        if n != self.numel():
+            raise RuntimeError("shape %s is invalid for an observation of %d elements" % (shape, self.numel()))
+        out = LazyObs(self.env, full)
+        out.version = self.version
+        return out
 
     view = reshape
 
