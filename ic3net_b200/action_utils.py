@@ -35,6 +35,25 @@ def parse_action_args(args):
 _ticks = {}
 
 
+def _joined_view(action_out, heads):
+    """The per-head log-prob tensors of CommNetMLP.forward are consecutive column slices of ONE contiguous float32
+    buffer: hand that buffer to the sampling kernel instead of concatenating the slices again (None: not the case)."""
+    first = action_out[0]
+    if first.dtype != torch.float32 or first.dim() != 3 or not first.is_cuda:
+        return None
+    atot = sum(heads)
+    B, N = first.shape[0], first.shape[1]
+    if first.stride() != (N * atot, atot, 1):
+        return None
+    base, off = first.data_ptr(), 0
+    for a, na in zip(action_out, heads):
+        if a.dtype != torch.float32 or a.shape[:2] != (B, N) or a.stride() != (N * atot, atot, 1) or \
+                a.data_ptr() != base + 4 * off:
+            return None
+        off += na
+    return torch.as_strided(first, (B, N, atot), (N * atot, atot, 1))
+
+
 def select_action(args, action_out, draws=None, tick=None):
     """action_out: list over heads of log-probs [B, N, na].  Returns int32 [B, N, heads].
 
@@ -43,9 +62,11 @@ def select_action(args, action_out, draws=None, tick=None):
     per-args call counter)."""
     if args.continuous:
         raise NotImplementedError("continuous actions are outside the accelerated path")
-    logp = torch.cat([a.to(torch.float32) for a in action_out], dim=-1).contiguous()
-    B, N = logp.shape[0], logp.shape[1]
     heads = [int(a.shape[-1]) for a in action_out]
+    logp = _joined_view(action_out, heads)            # CommNetMLP.forward returns views of one [B, N, sum(na)] buffer
+    if logp is None:
+        logp = torch.cat([a.to(torch.float32) for a in action_out], dim=-1).contiguous()
+    B, N = logp.shape[0], logp.shape[1]
     hd = (C.c_int32 * _lib.MAX_HEADS)(*(heads + [0] * (_lib.MAX_HEADS - len(heads))))
     cfg = _lib.PolicyCfg(B=B, N=N, H=32, O=1, nheads=len(heads), head_dim=hd, hard_attn=0, comm_avg=0,
                          comm_mask_zero=0, env_id0=int(getattr(args, 'env_id0', 0)),

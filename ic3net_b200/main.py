@@ -75,6 +75,9 @@ def build_parser():
     parser.add_argument('--nenvs', type=int, default=1024, help='environment slots per GPU')
     parser.add_argument('--obs_mode', default='index', choices=['index', 'dense'],
                         help='encoder fed from the env state (index) or from a materialised [B,N,O] observation (dense)')
+    parser.add_argument('--obs_api', default='dense', choices=['dense', 'handle'],
+                        help='what env.reset/step hand back: the dense [nenvs,N,obs_dim] tensor, or a LazyObs handle on the '
+                             'env state that CommNetMLP.forward consumes directly (lazy_obs.py)')
     parser.add_argument('--policy_impl', default=None, choices=['tc', 'simt'], help='tcgen05 or fp32 SIMT policy kernels')
     parser.add_argument('--grad_impl', default='autograd', choices=['autograd', 'manual'],
                         help='compute_grad through torch autograd recompute (default) or the explicit backward formulas')
