@@ -391,10 +391,10 @@ def gpu_arm(opts):
         # ic3net_b200/lazy_obs.py: env.step returns a LazyObs, CommNetMLP.forward evaluates the encoder from the state,
         # bit-identical x); the dense-tensor form of the same API is timed beside it
         ah, envh, neth, trh = build(opts.obs_mode, obs_api="handle")
-        mine = e2e_loop(ah, envh, neth, min(max(K, 50), 200), np, torch, select_action)
+        mine = e2e_loop(ah, envh, neth, min(max(K, 300), 600), np, torch, select_action)
         mine["obs_api"] = "handle"
         del trh
-        dense_e2e = e2e_loop(a, env, net, min(max(K, 50), 100), np, torch, select_action)
+        dense_e2e = e2e_loop(a, env, net, min(max(K, 100), 200), np, torch, select_action)
         mine["dense_obs_api"] = dict(value=dense_e2e["value"], ms_per_step=dense_e2e["ms_per_step"],
                                      note="same loop with env.step returning the dense [B,N,O] tensor (per rank)")
         if world > 1:
