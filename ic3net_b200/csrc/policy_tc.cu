@@ -213,7 +213,7 @@ int ic3_tc_policy_step(const ic3_policy_cfg* cfg, const ic3_policy_packed* w, co
   if (src.table && !src.split) return IC3_E_RANGE;      // the table IS the first of the two sums
   prof_mark(0, s);
   if (io->x) {
-    IC3_LAUNCH_RC(ic3_launch_pdl(prep_kernel<XSRC_TENSOR, false>, dim3(2 * ntiles_pad), dim3(256), 0, s, *cfg, *io, img, src, PrepBwd{}));
+    IC3_LAUNCH_RC(ic3_launch_pdl(prep_kernel<XSRC_TENSOR, false>, dim3(2 * ntiles_pad), dim3(PREP_THREADS), prep_T_bytes(cfg->N), s, *cfg, *io, img, src, PrepBwd{}));
   } else if (io->pp_env && io->pp_state) {       // fused index encoder, predator-prey
     const int W = 2 * io->pp_env->vision + 1;
     if (W * W > PREP_MAX_WW || io->pp_env->B != cfg->B || io->pp_env->N != cfg->N) return IC3_E_RANGE;
@@ -222,15 +222,15 @@ int ic3_tc_policy_step(const ic3_policy_cfg* cfg, const ic3_policy_packed* w, co
     src.pps = *io->pp_state;
     if (int lrc = ic3_pp_layout_check(io->pp_env, cfg)) return lrc;
     if (src.table) {
-      IC3_LAUNCH_RC(ic3_launch_pdl(prep_kernel<XSRC_PP, true>, dim3(2 * ntiles_pad), dim3(256), 0, s, *cfg, *io, img, src, PrepBwd{}));
+      IC3_LAUNCH_RC(ic3_launch_pdl(prep_kernel<XSRC_PP, true>, dim3(2 * ntiles_pad), dim3(PREP_THREADS), prep_T_bytes(cfg->N), s, *cfg, *io, img, src, PrepBwd{}));
     } else {
       static bool cfgd = false;
       if (!cfgd) {
-        cudaError_t e = cudaFuncSetAttribute(prep_kernel<XSRC_PP, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, PREP_X_BYTES);
+        cudaError_t e = cudaFuncSetAttribute(prep_kernel<XSRC_PP, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, PREP_X_BYTES + (PREP_ROWS + 2) * TC_H * 4);
         if (e != cudaSuccess) return (int)e;
         cfgd = true;
       }
-      IC3_LAUNCH_RC(ic3_launch_pdl(prep_kernel<XSRC_PP, false>, dim3(2 * ntiles_pad), dim3(256), PREP_X_BYTES, s, *cfg, *io, img, src, PrepBwd{}));
+      IC3_LAUNCH_RC(ic3_launch_pdl(prep_kernel<XSRC_PP, false>, dim3(2 * ntiles_pad), dim3(256), PREP_X_BYTES + prep_T_bytes(cfg->N), s, *cfg, *io, img, src, PrepBwd{}));
     }
   } else if (io->tj_env && io->tj_state) {       // fused index encoder, traffic junction
     const int W = 2 * io->tj_env->vision + 1;
@@ -240,15 +240,15 @@ int ic3_tc_policy_step(const ic3_policy_cfg* cfg, const ic3_policy_packed* w, co
     src.tjs = *io->tj_state;
     if (int lrc = ic3_tj_layout_check(io->tj_env, cfg)) return lrc;
     if (src.table) {
-      IC3_LAUNCH_RC(ic3_launch_pdl(prep_kernel<XSRC_TJ, true>, dim3(2 * ntiles_pad), dim3(256), 0, s, *cfg, *io, img, src, PrepBwd{}));
+      IC3_LAUNCH_RC(ic3_launch_pdl(prep_kernel<XSRC_TJ, true>, dim3(2 * ntiles_pad), dim3(PREP_THREADS), prep_T_bytes(cfg->N), s, *cfg, *io, img, src, PrepBwd{}));
     } else {
       static bool cfgd = false;
       if (!cfgd) {
-        cudaError_t e = cudaFuncSetAttribute(prep_kernel<XSRC_TJ, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, PREP_X_BYTES);
+        cudaError_t e = cudaFuncSetAttribute(prep_kernel<XSRC_TJ, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, PREP_X_BYTES + (PREP_ROWS + 2) * TC_H * 4);
         if (e != cudaSuccess) return (int)e;
         cfgd = true;
       }
-      IC3_LAUNCH_RC(ic3_launch_pdl(prep_kernel<XSRC_TJ, false>, dim3(2 * ntiles_pad), dim3(256), PREP_X_BYTES, s, *cfg, *io, img, src, PrepBwd{}));
+      IC3_LAUNCH_RC(ic3_launch_pdl(prep_kernel<XSRC_TJ, false>, dim3(2 * ntiles_pad), dim3(256), PREP_X_BYTES + prep_T_bytes(cfg->N), s, *cfg, *io, img, src, PrepBwd{}));
     }
   } else {
     return IC3_E_NULL;

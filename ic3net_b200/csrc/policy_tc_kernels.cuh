@@ -91,7 +91,8 @@ __global__ void pack_tc_kernel(ic3_policy_params p, __half* __restrict__ img, fl
 // 8 rows x 4 float4 columns so every store instruction writes two complete 128-byte core
 // matrices, with S_k = g_k (T - h_k) / (n_alive - 1).
 constexpr int PREP_ROWS = 64;      // rows per CTA (half a tile): 2 x more CTAs in flight than tiles
-constexpr int PREP_MAX_ENV = 34;   // environments touching 64 rows when N >= 2
+constexpr int PREP_THREADS = 160;  // 40 registers x 160 threads -> 10 CTAs/SM: the 1280 half-tile CTAs of a c2 step form ONE wave on 148 SMs (256 threads: 8 CTAs/SM = 1184 slots, a second wave of 96 CTAs)
+__host__ __device__ inline size_t prep_T_bytes(int N) { return (size_t)(PREP_ROWS / N + 2) * TC_H * sizeof(float); }
 constexpr int PREP_MAX_WW = 25;    // window cells (vision <= 2) the fused index encoder supports
 constexpr int PREP_X_BYTES = PREP_ROWS * TC_H * 4;   // shared-memory x tile of the fused index encoder
 
@@ -144,7 +145,8 @@ __global__ void __launch_bounds__(256) prep_kernel(ic3_policy_cfg cfg, ic3_polic
   static_assert(!BWD || TAB, "the backward pass uses the per-position table form of the encoder");
   __shared__ float s_gate[PREP_ROWS + 64];
   __shared__ float s_den[PREP_ROWS + 64];
-  __shared__ __align__(16) float s_T[PREP_MAX_ENV][TC_H];
+  // s_T: gated hidden-state sum of every environment touching this CTA's rows, [PREP_ROWS / N + 2][H] floats at the
+  // start of the dynamic shared memory (sized by the launcher: a static [34][H] array would cap the kernel at 8 CTAs/SM)
   // fused index encoder: per (row, window cell) the feature index of the one-hot class and the counts
   __shared__ int s_feat[(XSRC == XSRC_TENSOR || TAB) ? 1 : PREP_ROWS * PREP_MAX_WW];
   __shared__ int s_cnt[XSRC == XSRC_TENSOR ? 1 : PREP_ROWS * PREP_MAX_WW];
@@ -152,7 +154,9 @@ __global__ void __launch_bounds__(256) prep_kernel(ic3_policy_cfg cfg, ic3_polic
   __shared__ int s_pos[TAB ? PREP_ROWS : 1];          // table row of the agent (-1: observation is all zero)
   __shared__ float s_la[XSRC == XSRC_TJ ? PREP_ROWS : 1], s_ri[XSRC == XSRC_TJ ? PREP_ROWS : 1];
   __shared__ int s_live[XSRC == XSRC_TJ ? PREP_ROWS : 1];
-  extern __shared__ __align__(16) float s_x[];   // [PREP_ROWS][H] encoder output (index sources only)
+  extern __shared__ __align__(16) float s_dyn[];
+  float (*s_T)[TC_H] = reinterpret_cast<float (*)[TC_H]>(s_dyn);
+  float* s_x = s_dyn + (size_t)(PREP_ROWS / cfg.N + 2) * TC_H;   // [PREP_ROWS][H] encoder output (index sources without table)
   const int N = cfg.N;
   const int R = cfg.B * N;
   const int tile = blockIdx.x >> 1, hb = blockIdx.x & 1;
@@ -259,7 +263,7 @@ __global__ void __launch_bounds__(256) prep_kernel(ic3_policy_cfg cfg, ic3_polic
     const int gw = threadIdx.x >> 5, gl = threadIdx.x & 31;
     const float4* wq = reinterpret_cast<const float4*>(src.wT) + gl;
     const bool split = src.split != 0;
-    for (int rl = gw; rl < PREP_ROWS; rl += 8) {
+    for (int rl = gw; rl < PREP_ROWS; rl += (blockDim.x >> 5)) {
       float4 xv = __ldg(reinterpret_cast<const float4*>(src.bias) + gl);
       float4 x2 = make_float4(0.f, 0.f, 0.f, 0.f);
       const int row = row0 + rl;
@@ -321,7 +325,7 @@ __global__ void __launch_bounds__(256) prep_kernel(ic3_policy_cfg cfg, ic3_polic
     const int WW = XSRC == XSRC_PP ? (2 * src.pp.vision + 1) * (2 * src.pp.vision + 1)
                                    : (2 * src.tj.vision + 1) * (2 * src.tj.vision + 1);
     const int r8 = lane >> 2, c2 = (lane & 3) * 2;
-    for (int cm = warp; cm < bw.npg * 8; cm += 8) {
+    for (int cm = warp; cm < bw.npg * 8; cm += (blockDim.x >> 5)) {
       const int pg = cm >> 3, rgl = cm & 7;
       const int rl = rgl * 8 + r8, row = row0 + rl;
       float v[2] = {0.f, 0.f};
@@ -358,7 +362,7 @@ __global__ void __launch_bounds__(256) prep_kernel(ic3_policy_cfg cfg, ic3_polic
   const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
   const size_t tile_base = (size_t)tile * A_TILE_HALFS;
 #pragma unroll 2
-  for (int item = warp; item < 64; item += 8) {
+  for (int item = warp; item < 64; item += (blockDim.x >> 5)) {
     const int rcl = item & 7, qg = item >> 3;
     const int r8 = lane & 7, q = qg * 4 + (lane >> 3);
     const int rl = rcl * 8 + r8;                 // row inside this CTA's 64 rows
