@@ -291,3 +291,28 @@ def test_observation_handle_api_is_bit_identical_to_the_dense_tensor_api(name, i
     for a, b in zip(out["dense"], out["handle"]):
         for x, y in zip(a, b):
             assert np.array_equal(x, y)
+
+
+def test_graph_is_recaptured_when_the_curriculum_moves_the_spawn_rate():
+    """Kernel arguments passed by value (ic3_tj_cfg.spawn_thr) are frozen into a captured CUDA graph; the traffic-junction
+    curriculum (traffic_junction_env.py:196-200,620-626) changes that value between epochs.  The graph trainer must follow:
+    its rollouts equal an eager trainer's, epoch after epoch, and its add_rate statistic is the one the kernels used."""
+    meta, z = load_golden("ep_tj_medium_ic3net")
+    over = dict(add_rate_min=0.05, add_rate_max=0.5, curr_start=0, curr_end=4)
+    res = {}
+    for use_graph in (False, True):
+        args, env, net, tr, p = build(meta, 16, "index", use_graph=use_graph, seed=5, **over)
+        out = []
+        for epoch in (0, 1, 2, 3, 3, 6):
+            b = tr.rollout(20, epoch)
+            st = tr.collect_stat()
+            out.append((cpu(b.action).copy(), cpu(b.reward).copy(), cpu(b.alive_mask).copy(), st["add_rate"] / max(1, st["num_episodes"]),
+                        int(env.env.cfg.spawn_thr)))
+        res[use_graph] = out
+    rates = [o[3] for o in res[True]]
+    assert rates[0] < rates[1] < rates[2] < rates[3] == rates[4]            # the schedule really moved
+    for a, b in zip(res[False], res[True]):
+        assert a[3] == b[3] and a[4] == b[4]
+        assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2])
+    alive_first, alive_last = res[True][0][2].mean(), res[True][3][2].mean()
+    assert alive_last > alive_first                                          # more cars at the higher add_rate
