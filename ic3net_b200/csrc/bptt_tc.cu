@@ -36,7 +36,7 @@ constexpr int WG_MAX_NP = 512;                     // columns of P the weight-gr
 struct BpttScalars {      // device-resident scalars of the recursion
   unsigned dhmax;         // bits of max |dh| entering the next step to be processed (atomicMax on non-negative floats)
   unsigned dcmax;
-  unsigned hbound;        // bound of the heads' contribution to |dh| at the current step
+  unsigned hbound[2];     // bound of the heads' contribution to |dh| of step t, slot t & 1 (heads of step t - 1 run early)
   float cmax;             // max |c| over the whole record (set by the host once per compute_grad)
   float scale[2];         // s_t, indexed by t & 1: the weight-gradient kernel of step t runs on a side stream while
   float inv_scale[2];     // 1 / s_t          the main stream already prepares step t - 1
@@ -62,6 +62,7 @@ struct HeadsArgs {
   float* gw_part;             // [nblocks][8][H]  per-block partial sums of d head weights (block-private, += every step)
   double* gs_part;            // [nblocks][8 + 3] per-block: d head biases (8), action_loss, value_loss, entropy
   BpttScalars* sc;
+  int q;                      // t & 1
 };
 
 constexpr int HB_ROWS = 256;   // rows per block of the heads kernel
@@ -123,7 +124,7 @@ __global__ void __launch_bounds__(256) bptt_heads_kernel(HeadsArgs a) {
   for (int o = 0; o < BP_HEADS; ++o) hb += fabsf(d[o]) * s_wmax[o];
 #pragma unroll
   for (int s = 16; s > 0; s >>= 1) hb = fmaxf(hb, __shfl_xor_sync(IC3_FULL_MASK, hb, s));
-  if (lane == 0 && hb > 0.f) atomicMax(&a.sc->hbound, __float_as_uint(hb));
+  if (lane == 0 && hb > 0.f) atomicMax(&a.sc->hbound[a.q], __float_as_uint(hb));
   // block sums: bias gradients + losses (double)
   double v[BP_HEADS + 3];
 #pragma unroll
@@ -185,7 +186,7 @@ __global__ void __launch_bounds__(256) bptt_heads_kernel(HeadsArgs a) {
 
 // s_t = 2^e with  bound * s_t in (2^13, 2^14]:  |d gate| <= (|dc| + |dh|) * max(1, |c_prev| / 4)
 __global__ void bptt_scale_kernel(BpttScalars* sc, int q) {
-  const float dh = __uint_as_float(sc->dhmax) + __uint_as_float(sc->hbound);
+  const float dh = __uint_as_float(sc->dhmax) + __uint_as_float(sc->hbound[q]);
   const float dc = __uint_as_float(sc->dcmax);
   const float bound = (dh + dc) * fmaxf(1.f, 0.25f * sc->cmax);
   float s = 1.f;
@@ -200,7 +201,7 @@ __global__ void bptt_scale_kernel(BpttScalars* sc, int q) {
   sc->inv_scale[q] = 1.f / s;
   sc->dhmax = 0u;
   sc->dcmax = 0u;
-  sc->hbound = 0u;
+  sc->hbound[q] = 0u;
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -1072,8 +1073,9 @@ int sm_count() {
 // keeps everything on the caller's stream).
 struct BpttStreams {
   cudaStream_t side;
-  cudaEvent_t gates_done[2], wgrad_done[2];
+  cudaEvent_t gates_done[2], wgrad_done[2], prep_done[2], main_done[2];
   bool overlap;
+  int prepared_t[2];         // lock-step index whose heads / operand images occupy buffer set q (-1: none)
 };
 
 BpttStreams* bptt_streams() {
@@ -1082,10 +1084,13 @@ BpttStreams* bptt_streams() {
   if (state == 0) {
     const char* e = getenv("IC3_BPTT_OVERLAP");
     ss.overlap = !(e && atoi(e) == 0);
+    ss.prepared_t[0] = ss.prepared_t[1] = -1;
     bool ok = cudaStreamCreateWithFlags(&ss.side, cudaStreamNonBlocking) == cudaSuccess;
     for (int k = 0; k < 2 && ok; ++k) {
       ok = cudaEventCreateWithFlags(&ss.gates_done[k], cudaEventDisableTiming) == cudaSuccess &&
-           cudaEventCreateWithFlags(&ss.wgrad_done[k], cudaEventDisableTiming) == cudaSuccess;
+           cudaEventCreateWithFlags(&ss.wgrad_done[k], cudaEventDisableTiming) == cudaSuccess &&
+           cudaEventCreateWithFlags(&ss.prep_done[k], cudaEventDisableTiming) == cudaSuccess &&
+           cudaEventCreateWithFlags(&ss.main_done[k], cudaEventDisableTiming) == cudaSuccess;
     }
     state = ok ? 1 : -1;
   }
@@ -1127,11 +1132,11 @@ int plan_layout(const ic3_policy_cfg* cfg, int npos, int WW, int is_tj, Layout* 
   L->img_stride = off;
   take(off);                                   // second set: same sizes, same order
   L->w2_img = take(W2_IMG_HALFS * 2);
-  L->dout = take((size_t)L->ntiles * TC_M * BP_HEADS * 4);
+  L->dout = take((size_t)2 * L->ntiles * TC_M * BP_HEADS * 4);         // [2]: heads of step t - 1 run while step t reads
   L->dSs = take((size_t)L->ntiles * TC_M * TC_H * 4);
   L->dh_direct = take((size_t)L->ntiles * TC_M * TC_H * 4);
-  L->gs = take((size_t)L->ntiles * TC_M * 4);
-  L->gr = take((size_t)L->ntiles * TC_M * 4);
+  L->gs = take((size_t)2 * L->ntiles * TC_M * 4);                       // [2] by step parity, like the images
+  L->gr = take((size_t)2 * L->ntiles * TC_M * 4);
   L->partial = take((size_t)L->ncta_wg * 512 * 128 * 4);
   L->gw_part = take((size_t)L->nhb * BP_HEADS * TC_H * 4);
   L->gs_part = take((size_t)L->nhb * (BP_HEADS + 3) * 8);
@@ -1198,6 +1203,9 @@ extern "C" int ic3_bptt_begin(const ic3_bptt_plan* p, float cmax, void* stream) 
   bptt_pack_w2_kernel<<<(256 * 512 + 255) / 256, 256, 0, s>>>(reinterpret_cast<const __half*>(p->w->lstm_img),
                                                               reinterpret_cast<__half*>(ws + L.w2_img));
   IC3_LAUNCH_CHECK();
+  BpttStreams* ss = bptt_streams();
+  if (!ss) return IC3_E_UNSUPPORTED;
+  ss->prepared_t[0] = ss->prepared_t[1] = -1;
   BpttScalars init;
   memset(&init, 0, sizeof(init));
   init.cmax = cmax;
@@ -1205,40 +1213,29 @@ extern "C" int ic3_bptt_begin(const ic3_bptt_plan* p, float cmax, void* stream) 
   init.inv_scale[0] = init.inv_scale[1] = 1.f;
   e = cudaMemcpyAsync(ws + L.sc, &init, sizeof(init), cudaMemcpyHostToDevice, s);
   if (e != cudaSuccess) return (int)e;
+  // the look-ahead kernels of the first two steps (side stream) must see the zeroed accumulators -- and everything the
+  // caller enqueued before this call (returns, advantages, the rollout records)
+  for (int k = 0; k < 2; ++k) {
+    e = cudaEventRecord(ss->main_done[k], s);
+    if (e != cudaSuccess) return (int)e;
+  }
   return IC3_OK;
 }
 
-extern "C" int ic3_bptt_step(const ic3_bptt_plan* p, const ic3_bptt_step_io* io, void* stream) {
-  if (!p || !io || !p->cfg || !p->w || !p->workspace) return IC3_E_NULL;
-  if (!io->h_prev || !io->c_prev || !io->h_new || !io->logp || !io->action || !io->value || !io->ret || !io->adv ||
-      !io->alive_post || !io->dh || !io->dc)
-    return IC3_E_NULL;
+// Recursion-independent part of a step: d loss / d outputs from the records (heads) and the operand images of the
+// step (prep).  Runs on `s` into buffer set q = t & 1.
+static int bptt_prepare_on(const ic3_bptt_plan* p, const ic3_bptt_step_io* io, const Layout& L, int npos, int is_tj,
+                           cudaStream_t s) {
   const ic3_policy_cfg* cfg = p->cfg;
-  if (cfg->H != TC_H) return IC3_E_UNSUPPORTED;
-  int npos, WW, is_tj;
-  int rc = env_geometry(p, &npos, &WW, &is_tj);
-  if (rc) return rc;
-  Layout L;
-  rc = plan_layout(cfg, npos, WW, is_tj, &L);
-  if (rc) return rc;
-  cudaStream_t s = (cudaStream_t)stream;
   unsigned char* ws = reinterpret_cast<unsigned char*>(p->workspace);
   const int R = cfg->B * cfg->N;
   int atot = 0;
   for (int k = 0; k < cfg->nheads; ++k) atot += cfg->head_dim[k];
-  const int nout = 1 + atot;
-  if (nout > BP_HEADS) return IC3_E_UNSUPPORTED;
   BpttScalars* sc = reinterpret_cast<BpttScalars*>(ws + L.sc);
   const int q = io->t & 1;
+  const size_t rows_pad = (size_t)L.ntiles * TC_M;
   __half* a_img = reinterpret_cast<__half*>(ws + L.a_img + (size_t)q * L.img_stride);
   __half* p_img = reinterpret_cast<__half*>(ws + L.p_img + (size_t)q * L.img_stride);
-  __half* dg_img = reinterpret_cast<__half*>(ws + L.dg_img + (size_t)q * L.img_stride);
-  BpttStreams* ss = bptt_streams();
-  if (!ss) return IC3_E_UNSUPPORTED;
-  // image set q was last read by the weight-gradient kernel of step t + 2 (side stream)
-  cudaError_t se = cudaStreamWaitEvent(s, ss->wgrad_done[q], 0);
-  if (se != cudaSuccess) return (int)se;
-
   // ---- heads ----
   HeadsArgs ha;
   memset(&ha, 0, sizeof(ha));
@@ -1247,15 +1244,13 @@ extern "C" int ic3_bptt_step(const ic3_bptt_plan* p, const ic3_bptt_step_io* io,
   ha.value_coeff = p->value_coeff; ha.entr = p->entr;
   ha.logp = io->logp; ha.action = io->action; ha.value = io->value; ha.ret = io->ret; ha.adv = io->adv;
   ha.alive_post = io->alive_post; ha.valid = io->valid; ha.h_new = io->h_new; ha.head_w = p->w->head_w;
-  ha.dout = reinterpret_cast<float*>(ws + L.dout);
+  ha.dout = reinterpret_cast<float*>(ws + L.dout) + (size_t)q * rows_pad * BP_HEADS;
   ha.gw_part = reinterpret_cast<float*>(ws + L.gw_part);
   ha.gs_part = reinterpret_cast<double*>(ws + L.gs_part);
   ha.sc = sc;
+  ha.q = q;
   bptt_heads_kernel<<<L.nhb, 256, 0, s>>>(ha);
   IC3_LAUNCH_CHECK();
-  bptt_scale_kernel<<<1, 1, 0, s>>>(sc, q);
-  IC3_LAUNCH_CHECK();
-
   // ---- operand images of step t from the records ----
   ic3_policy_io pio;
   memset(&pio, 0, sizeof(pio));
@@ -1269,8 +1264,8 @@ extern "C" int ic3_bptt_step(const ic3_bptt_plan* p, const ic3_bptt_step_io* io,
   if (!src.table || !src.split) return IC3_E_NULL;
   PrepBwd bw;
   bw.p_img = p_img;
-  bw.gs = reinterpret_cast<float*>(ws + L.gs);
-  bw.gr = reinterpret_cast<float*>(ws + L.gr);
+  bw.gs = reinterpret_cast<float*>(ws + L.gs) + (size_t)q * rows_pad;
+  bw.gr = reinterpret_cast<float*>(ws + L.gr) + (size_t)q * rows_pad;
   bw.npg = L.np / 8;
   bw.npos = npos;
   const int ntiles = L.ntiles;
@@ -1290,6 +1285,82 @@ extern "C" int ic3_bptt_step(const ic3_bptt_plan* p, const ic3_bptt_step_io* io,
     src.tjs.route_id = const_cast<int32_t*>(io->tj_route_id);
     IC3_LAUNCH_RC(ic3_launch_pdl(prep_kernel<XSRC_TJ, true, true>, dim3(2 * ntiles), dim3(PREP_THREADS), prep_T_bytes(cfg->N), s, *cfg, pio, a_img, src, bw));
   }
+  return IC3_OK;
+}
+
+static int bptt_common(const ic3_bptt_plan* p, const ic3_bptt_step_io* io, Layout* L, int* npos, int* is_tj) {
+  if (!p || !io || !p->cfg || !p->w || !p->workspace) return IC3_E_NULL;
+  if (!io->h_prev || !io->c_prev || !io->h_new || !io->logp || !io->action || !io->value || !io->ret || !io->adv ||
+      !io->alive_post || !io->dh || !io->dc)
+    return IC3_E_NULL;
+  if (p->cfg->H != TC_H) return IC3_E_UNSUPPORTED;
+  int WW;
+  int rc = env_geometry(p, npos, &WW, is_tj);
+  if (rc) return rc;
+  rc = plan_layout(p->cfg, *npos, WW, *is_tj, L);
+  if (rc) return rc;
+  int nout = 1;
+  for (int k = 0; k < p->cfg->nheads; ++k) nout += p->cfg->head_dim[k];
+  return nout > BP_HEADS ? IC3_E_UNSUPPORTED : IC3_OK;
+}
+
+// Optional: launch the recursion-independent kernels of step io->t (heads, operand images) AHEAD of ic3_bptt_step(t),
+// on the library's side stream, so that they overlap the tensor-core kernels of step t + 1 (which leave one CTA slot
+// per SM free).  `stream` is the stream ic3_bptt_step will be called on.  Without this call (or with
+// IC3_BPTT_OVERLAP=0) ic3_bptt_step runs them itself.
+extern "C" int ic3_bptt_prepare(const ic3_bptt_plan* p, const ic3_bptt_step_io* io, void* stream) {
+  Layout L;
+  int npos, is_tj;
+  int rc = bptt_common(p, io, &L, &npos, &is_tj);
+  if (rc) return rc;
+  BpttStreams* ss = bptt_streams();
+  if (!ss) return IC3_E_UNSUPPORTED;
+  if (!ss->overlap) return IC3_OK;                  // ic3_bptt_step will do it inline
+  const int q = io->t & 1;
+  // buffer set q was last used by step t + 2: its main-stream kernels (gates / dgrad / comm read A, dout, gs, gr) and
+  // its weight-gradient kernel (side stream, already ordered before this call)
+  cudaError_t e = cudaStreamWaitEvent(ss->side, ss->main_done[q], 0);
+  if (e != cudaSuccess) return (int)e;
+  rc = bptt_prepare_on(p, io, L, npos, is_tj, ss->side);
+  if (rc) return rc;
+  e = cudaEventRecord(ss->prep_done[q], ss->side);
+  if (e != cudaSuccess) return (int)e;
+  ss->prepared_t[q] = io->t;
+  return IC3_OK;
+}
+
+extern "C" int ic3_bptt_step(const ic3_bptt_plan* p, const ic3_bptt_step_io* io, void* stream) {
+  Layout L;
+  int npos, is_tj;
+  int rc = bptt_common(p, io, &L, &npos, &is_tj);
+  if (rc) return rc;
+  const ic3_policy_cfg* cfg = p->cfg;
+  cudaStream_t s = (cudaStream_t)stream;
+  unsigned char* ws = reinterpret_cast<unsigned char*>(p->workspace);
+  const int R = cfg->B * cfg->N;
+  int nout = 1;
+  for (int k = 0; k < cfg->nheads; ++k) nout += cfg->head_dim[k];
+  BpttScalars* sc = reinterpret_cast<BpttScalars*>(ws + L.sc);
+  const int q = io->t & 1;
+  const size_t rows_pad = (size_t)L.ntiles * TC_M;
+  const int ntiles = L.ntiles;
+  __half* a_img = reinterpret_cast<__half*>(ws + L.a_img + (size_t)q * L.img_stride);
+  __half* dg_img = reinterpret_cast<__half*>(ws + L.dg_img + (size_t)q * L.img_stride);
+  BpttStreams* ss = bptt_streams();
+  if (!ss) return IC3_E_UNSUPPORTED;
+  // buffer set q (images, scale) was last read by the weight-gradient kernel of step t + 2 (side stream)
+  cudaError_t se = cudaStreamWaitEvent(s, ss->wgrad_done[q], 0);
+  if (se != cudaSuccess) return (int)se;
+  if (ss->prepared_t[q] == io->t) {                 // heads + images were launched ahead (ic3_bptt_prepare)
+    se = cudaStreamWaitEvent(s, ss->prep_done[q], 0);
+    if (se != cudaSuccess) return (int)se;
+    ss->prepared_t[q] = -1;
+  } else {
+    rc = bptt_prepare_on(p, io, L, npos, is_tj, s);
+    if (rc) return rc;
+  }
+  bptt_scale_kernel<<<1, 1, 0, s>>>(sc, q);
+  IC3_LAUNCH_CHECK();
 
   // ---- gates ----
   {
@@ -1302,7 +1373,7 @@ extern "C" int ic3_bptt_step(const ic3_bptt_plan* p, const ic3_bptt_step_io* io,
     }
     GatesArgs ga;
     ga.R = R; ga.N = cfg->N; ga.c_prev = io->c_prev; ga.fresh = io->fresh; ga.cut = io->cut;
-    ga.dout = reinterpret_cast<const float*>(ws + L.dout); ga.dh = io->dh; ga.dc = io->dc; ga.dg_img = dg_img; ga.sc = sc;
+    ga.dout = reinterpret_cast<const float*>(ws + L.dout) + (size_t)q * rows_pad * BP_HEADS; ga.dh = io->dh; ga.dc = io->dc; ga.dg_img = dg_img; ga.sc = sc;
     ga.q = q;
     ga.err = io->err;
     const int nitems = 2 * ntiles;
@@ -1323,7 +1394,7 @@ extern "C" int ic3_bptt_step(const ic3_bptt_plan* p, const ic3_bptt_step_io* io,
       cfgd = true;
     }
     DgradArgs da;
-    da.R = R; da.gs = reinterpret_cast<const float*>(ws + L.gs); da.dSs = reinterpret_cast<float*>(ws + L.dSs);
+    da.R = R; da.gs = reinterpret_cast<const float*>(ws + L.gs) + (size_t)q * rows_pad; da.dSs = reinterpret_cast<float*>(ws + L.dSs);
     da.dh_direct = reinterpret_cast<float*>(ws + L.dh_direct); da.sc = sc; da.q = q; da.err = io->err;
     const int grid = ntiles < sm_count() ? ntiles : sm_count();
     bptt_dgrad_kernel<<<grid, TC_P_THREADS, smem, s>>>(da, dg_img, reinterpret_cast<const __half*>(ws + L.w2_img), ntiles);
@@ -1333,10 +1404,12 @@ extern "C" int ic3_bptt_step(const ic3_bptt_plan* p, const ic3_bptt_step_io* io,
   {
     CommArgs ca;
     ca.B = cfg->B; ca.N = cfg->N; ca.dSs = reinterpret_cast<const float*>(ws + L.dSs);
-    ca.dh_direct = reinterpret_cast<const float*>(ws + L.dh_direct); ca.gr = reinterpret_cast<const float*>(ws + L.gr);
+    ca.dh_direct = reinterpret_cast<const float*>(ws + L.dh_direct); ca.gr = reinterpret_cast<const float*>(ws + L.gr) + (size_t)q * rows_pad;
     ca.fresh = io->fresh; ca.no_comm = cfg->comm_mask_zero || cfg->N < 2; ca.dh = io->dh; ca.sc = sc;
     bptt_comm_kernel<<<(cfg->B + 7) / 8, 256, 0, s>>>(ca);
     IC3_LAUNCH_CHECK();
+    se = cudaEventRecord(ss->main_done[q], s);          // buffer set q may be refilled for step t - 2 once wgrad(t) is done too
+    if (se != cudaSuccess) return (int)se;
   }
   // ---- weight gradients: on the side stream, overlapping the small kernels of this and the next step ----
   {

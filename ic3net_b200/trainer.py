@@ -602,20 +602,31 @@ class Trainer(object):
         st['dc'].zero_()
         _lib.check(lib.ic3_bptt_begin(C.byref(plan), cmax, s))
         value = b['value']
+
+        def step_io(t):
+            return _lib.BpttStepIO(t=t, h_prev=b['rec_h'][t].data_ptr(), c_prev=b['rec_c'][t].data_ptr(),
+                                   h_new=b['rec_h'][t + 1].data_ptr(), fresh=b['s_fresh'][t].data_ptr(),
+                                   comm=b['s_comm'][t].data_ptr() if hard else None, alive=b['s_alive'][t].data_ptr(),
+                                   cut=cut[t].data_ptr() if cut is not None else None,
+                                   pp_loc=None if self.is_tj else b['s_loc'][t].data_ptr(),
+                                   tj_loc=b['s_tjloc'][t].data_ptr() if self.is_tj else None,
+                                   tj_alive=b['s_tjalive'][t].data_ptr() if self.is_tj else None,
+                                   tj_last_act=b['s_tjlast'][t].data_ptr() if self.is_tj else None,
+                                   tj_route_id=b['s_tjroute'][t].data_ptr() if self.is_tj else None,
+                                   logp=b['logp'][t].data_ptr(), action=b['action'][t].data_ptr(),
+                                   value=value[t].data_ptr(), ret=ret[t].data_ptr(), adv=adv[t].data_ptr(),
+                                   alive_post=b['ralive'][t].data_ptr(), valid=b['valid'][t].data_ptr(),
+                                   dh=st['dh'].data_ptr(), dc=st['dc'].data_ptr(), err=b['err'].data_ptr())
+        # look-ahead: the heads gradient and the operand images of step t - 1 do not depend on the recursion; they are
+        # launched on the library's side stream before step t and overlap its tensor-core kernels
+        nxt = step_io(T - 1) if T > 0 else None
+        if nxt is not None:
+            _lib.check(lib.ic3_bptt_prepare(C.byref(plan), C.byref(nxt), s))
         for t in reversed(range(T)):
-            io = _lib.BpttStepIO(t=t, h_prev=b['rec_h'][t].data_ptr(), c_prev=b['rec_c'][t].data_ptr(),
-                                 h_new=b['rec_h'][t + 1].data_ptr(), fresh=b['s_fresh'][t].data_ptr(),
-                                 comm=b['s_comm'][t].data_ptr() if hard else None, alive=b['s_alive'][t].data_ptr(),
-                                 cut=cut[t].data_ptr() if cut is not None else None,
-                                 pp_loc=None if self.is_tj else b['s_loc'][t].data_ptr(),
-                                 tj_loc=b['s_tjloc'][t].data_ptr() if self.is_tj else None,
-                                 tj_alive=b['s_tjalive'][t].data_ptr() if self.is_tj else None,
-                                 tj_last_act=b['s_tjlast'][t].data_ptr() if self.is_tj else None,
-                                 tj_route_id=b['s_tjroute'][t].data_ptr() if self.is_tj else None,
-                                 logp=b['logp'][t].data_ptr(), action=b['action'][t].data_ptr(),
-                                 value=value[t].data_ptr(), ret=ret[t].data_ptr(), adv=adv[t].data_ptr(),
-                                 alive_post=b['ralive'][t].data_ptr(), valid=b['valid'][t].data_ptr(),
-                                 dh=st['dh'].data_ptr(), dc=st['dc'].data_ptr(), err=b['err'].data_ptr())
+            io = nxt
+            if t > 0:
+                nxt = step_io(t - 1)
+                _lib.check(lib.ic3_bptt_prepare(C.byref(plan), C.byref(nxt), s))
             _lib.check(lib.ic3_bptt_step(C.byref(plan), C.byref(io), s))
         # parameter gradients are ADDED to the .grad buffers (flat views of FlatRMSprop)
         params, grads = self._param_structs()

@@ -434,6 +434,11 @@ typedef struct {
 uint64_t ic3_bptt_workspace_bytes(const ic3_bptt_plan* plan);   /* 0 = configuration not supported by the kernels */
 int ic3_bptt_begin(const ic3_bptt_plan* plan, float c_abs_max, void* stream);
 int ic3_bptt_step(const ic3_bptt_plan* plan, const ic3_bptt_step_io* io, void* stream);
+/* Optional look-ahead: launches the recursion-independent kernels of step io->t (heads gradient, operand images) on the
+ * library's side stream so that they overlap the tensor-core kernels of step t + 1; call it for step t - 1 right before
+ * ic3_bptt_step(t) (and once for t = T - 1 after ic3_bptt_begin).  The step's records must not change until
+ * ic3_bptt_step(io->t) has been issued. */
+int ic3_bptt_prepare(const ic3_bptt_plan* plan, const ic3_bptt_step_io* io, void* stream);
 /* params: the CURRENT parameters; grads: same struct holding the gradient buffers (reference layouts);
  * losses: device double[3] = action_loss, value_loss, entropy sums (trainer.py:198-216). */
 int ic3_bptt_finish(const ic3_bptt_plan* plan, const ic3_policy_params* params, const ic3_policy_params* grads,
