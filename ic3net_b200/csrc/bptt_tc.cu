@@ -67,7 +67,9 @@ struct HeadsArgs {
 
 constexpr int HB_ROWS = 256;   // rows per block of the heads kernel
 
-__global__ void __launch_bounds__(256) bptt_heads_kernel(HeadsArgs a) {
+// <= 36 registers: one CTA of this kernel fits beside a resident bptt_gates_kernel CTA (576 threads x 96 registers), so it
+// overlaps the tensor-core kernels of the previous step when launched ahead on the side stream (ic3_bptt_prepare)
+__global__ void __launch_bounds__(256, 7) bptt_heads_kernel(HeadsArgs a) {
   __shared__ __align__(16) float s_dout[HB_ROWS][BP_HEADS];
   __shared__ float s_wmax[BP_HEADS];
   __shared__ double s_red[8][BP_HEADS + 3];
@@ -1236,21 +1238,6 @@ static int bptt_prepare_on(const ic3_bptt_plan* p, const ic3_bptt_step_io* io, c
   const size_t rows_pad = (size_t)L.ntiles * TC_M;
   __half* a_img = reinterpret_cast<__half*>(ws + L.a_img + (size_t)q * L.img_stride);
   __half* p_img = reinterpret_cast<__half*>(ws + L.p_img + (size_t)q * L.img_stride);
-  // ---- heads ----
-  HeadsArgs ha;
-  memset(&ha, 0, sizeof(ha));
-  ha.R = R; ha.N = cfg->N; ha.nheads = cfg->nheads; ha.atot = atot;
-  for (int k = 0; k < IC3_MAX_HEADS; ++k) ha.head_dim[k] = cfg->head_dim[k];
-  ha.value_coeff = p->value_coeff; ha.entr = p->entr;
-  ha.logp = io->logp; ha.action = io->action; ha.value = io->value; ha.ret = io->ret; ha.adv = io->adv;
-  ha.alive_post = io->alive_post; ha.valid = io->valid; ha.h_new = io->h_new; ha.head_w = p->w->head_w;
-  ha.dout = reinterpret_cast<float*>(ws + L.dout) + (size_t)q * rows_pad * BP_HEADS;
-  ha.gw_part = reinterpret_cast<float*>(ws + L.gw_part);
-  ha.gs_part = reinterpret_cast<double*>(ws + L.gs_part);
-  ha.sc = sc;
-  ha.q = q;
-  bptt_heads_kernel<<<L.nhb, 256, 0, s>>>(ha);
-  IC3_LAUNCH_CHECK();
   // ---- operand images of step t from the records ----
   ic3_policy_io pio;
   memset(&pio, 0, sizeof(pio));
@@ -1285,6 +1272,21 @@ static int bptt_prepare_on(const ic3_bptt_plan* p, const ic3_bptt_step_io* io, c
     src.tjs.route_id = const_cast<int32_t*>(io->tj_route_id);
     IC3_LAUNCH_RC(ic3_launch_pdl(prep_kernel<XSRC_TJ, true, true>, dim3(2 * ntiles), dim3(PREP_THREADS), prep_T_bytes(cfg->N), s, *cfg, pio, a_img, src, bw));
   }
+  // ---- heads ----
+  HeadsArgs ha;
+  memset(&ha, 0, sizeof(ha));
+  ha.R = R; ha.N = cfg->N; ha.nheads = cfg->nheads; ha.atot = atot;
+  for (int k = 0; k < IC3_MAX_HEADS; ++k) ha.head_dim[k] = cfg->head_dim[k];
+  ha.value_coeff = p->value_coeff; ha.entr = p->entr;
+  ha.logp = io->logp; ha.action = io->action; ha.value = io->value; ha.ret = io->ret; ha.adv = io->adv;
+  ha.alive_post = io->alive_post; ha.valid = io->valid; ha.h_new = io->h_new; ha.head_w = p->w->head_w;
+  ha.dout = reinterpret_cast<float*>(ws + L.dout) + (size_t)q * rows_pad * BP_HEADS;
+  ha.gw_part = reinterpret_cast<float*>(ws + L.gw_part);
+  ha.gs_part = reinterpret_cast<double*>(ws + L.gs_part);
+  ha.sc = sc;
+  ha.q = q;
+  bptt_heads_kernel<<<L.nhb, 256, 0, s>>>(ha);
+  IC3_LAUNCH_CHECK();
   return IC3_OK;
 }
 
