@@ -115,6 +115,17 @@ class PredatorPreyEnv(object):
     def _new_obs(self):
         return torch.empty(self.obs_shape, dtype=torch.float32, device=self.device)
 
+    _STATE = ('loc', 'reached_prey', 'done', 'success', 'episode', 'tick')
+
+    def snapshot(self):
+        """Copy of the whole device state of the batch (positions, flags, RNG counters): restore() rewinds to it."""
+        return [getattr(self, k).clone() for k in self._STATE]
+
+    def restore(self, snap):
+        for k, v in zip(self._STATE, snap):
+            getattr(self, k).copy_(v)
+        self.obs_version += 1
+
     def _obs_handle(self):
         from .lazy_obs import LazyObs
         return LazyObs(self)

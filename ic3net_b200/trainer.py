@@ -359,9 +359,17 @@ class Trainer(object):
             # 196-200,620-626; a re-seeded env changes cfg.seed) and a stale graph is re-captured
             key = (T, int(quota), int(getattr(e.cfg, 'spawn_thr', 0)), int(e.cfg.seed), int(e.cfg.env_id0))
             if self._graph is None or self._graph_key != key:
-                self._enqueue(T, quota)           # warm-up (lazy function attributes, allocator)
+                # warm-up pass (lazy function attributes, allocator) on a snapshot of the env state, rewound afterwards:
+                # the captured pass then starts from exactly the state an eager rollout would start from (same RNG ticks)
+                snap = e.snapshot()
+                keys = ('fresh', 'comm', 'alive', 't_ep', 'h', 'c', 'halted', 'stat_reward', 'stat_comm', 'stat_success',
+                        'stat_episodes', 'stat_steps')
+                saved = {k: b[k].clone() for k in keys}
+                self._enqueue(T, quota)
                 torch.cuda.synchronize()
-                self._episode_boundary(epoch)
+                e.restore(snap)                   # env state, RNG ticks ...
+                for k, v in saved.items():        # ... and the trainer-side episode state, as the boundary above left them
+                    b[k].copy_(v)
                 g = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(g):
                     self._enqueue(T, quota)

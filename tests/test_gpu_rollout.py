@@ -123,22 +123,20 @@ def test_lockstep_rollout_matches_oracle(name, B, T, impl):
 
 
 def test_graph_replay_equals_eager():
-    """The graph trainer's first call = warm-up pass + captured pass, its second call = one
-    replay; so its second call must equal an eager trainer's third rollout bit for bit."""
+    """The graph trainer (warm-up on a rewound snapshot, capture, replay) produces bit for bit what the eager trainer
+    produces, rollout after rollout."""
     meta, z = load_golden("ep_tj_medium_ic3net")
-    args, env, net, tr, p = build(meta, 16, "index", use_graph=True, seed=5)
-    tr.rollout(40, 0)
-    bg = tr.rollout(40, 0)
-    torch.cuda.synchronize()
-    g = (cpu(bg.action).copy(), cpu(bg.reward).copy(), cpu(bg.value).copy())
-    args, env, net, tr, p = build(meta, 16, "index", use_graph=False, seed=5)
-    tr.rollout(40, 0)
-    tr.rollout(40, 0)
-    b3 = tr.rollout(40, 0)
-    torch.cuda.synchronize()
-    assert np.array_equal(cpu(b3.action), g[0])
-    assert np.array_equal(cpu(b3.reward), g[1])
-    assert np.array_equal(cpu(b3.value), g[2])
+    res = {}
+    for use_graph in (True, False):
+        args, env, net, tr, p = build(meta, 16, "index", use_graph=use_graph, seed=5)
+        out = []
+        for k in range(3):
+            b = tr.rollout(40, 0)
+            torch.cuda.synchronize()
+            out.append((cpu(b.action).copy(), cpu(b.reward).copy(), cpu(b.value).copy()))
+        res[use_graph] = out
+    for a, b in zip(res[True], res[False]):
+        assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2])
 
 
 @pytest.mark.parametrize("name", ["ep_pp_hard_ic3net", "ep_tj_medium_ic3net", "ep_tj_medium_v1_commnet"])
