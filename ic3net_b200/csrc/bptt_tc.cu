@@ -1099,6 +1099,14 @@ BpttStreams* bptt_streams() {
   return state == 1 ? &ss : nullptr;
 }
 
+// The persistent tensor-core kernels leave ~30 KB of an SM's shared memory unused; with the carve-out pinned to the
+// maximum (instead of the smallest configuration that fits the kernel) one CTA of the look-ahead kernels (operand images,
+// heads gradient) can be resident beside them.
+template <typename K>
+cudaError_t prefer_max_smem(K kern) {
+  return cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+}
+
 struct Layout {         // of the workspace, in bytes
   size_t a_img, p_img, dg_img, img_stride, w2_img, dout, dSs, dh_direct, gs, gr, partial, gw_part, gs_part, sc, G, Y, GSC, dC, wj, cw, losses,
       total;
@@ -1371,6 +1379,7 @@ extern "C" int ic3_bptt_step(const ic3_bptt_plan* p, const ic3_bptt_step_io* io,
     if (!cfgd) {
       cudaError_t e = cudaFuncSetAttribute(bptt_gates_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       if (e != cudaSuccess) return (int)e;
+      prefer_max_smem(bptt_gates_kernel);
       cfgd = true;
     }
     GatesArgs ga;
@@ -1393,6 +1402,7 @@ extern "C" int ic3_bptt_step(const ic3_bptt_plan* p, const ic3_bptt_step_io* io,
     if (!cfgd) {
       cudaError_t e = cudaFuncSetAttribute(bptt_dgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       if (e != cudaSuccess) return (int)e;
+      prefer_max_smem(bptt_dgrad_kernel);
       cfgd = true;
     }
     DgradArgs da;
@@ -1424,6 +1434,11 @@ extern "C" int ic3_bptt_step(const ic3_bptt_plan* p, const ic3_bptt_step_io* io,
     if (!cfgd) {
       cudaError_t e = cudaFuncSetAttribute(bptt_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
       if (e != cudaSuccess) return (int)e;
+      prefer_max_smem(bptt_wgrad_kernel);
+      prefer_max_smem(bptt_heads_kernel);
+      prefer_max_smem(bptt_comm_kernel);
+      prefer_max_smem(prep_kernel<XSRC_PP, true, true>);
+      prefer_max_smem(prep_kernel<XSRC_TJ, true, true>);
       cfgd = true;
     }
     if (smem > 200 * 1024) return IC3_E_UNSUPPORTED;
