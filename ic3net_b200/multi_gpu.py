@@ -181,7 +181,7 @@ class MultiGPUTrainer(object):
         tr = self.trainer
         if hasattr(tr, 'stat_vector') and hasattr(tr.optimizer, 'flat_grads'):
             T, quota = tr.batch_plan()
-            batch = tr.rollout(T, epoch, quota=quota)            # no host synchronisation up to reduce_device
+            batch = tr.rollout(T, epoch, quota=quota)            # statistics stay on the device up to reduce_device
             tr.optimizer.zero_grad(set_to_none=False)
             loss_vec = tr.compute_grad_device(batch)
             stat = self.reduce_device(loss_vec)

@@ -574,8 +574,9 @@ class Trainer(object):
         return tot
 
     def _compute_grad_kernels(self, adv, ret):
-        """Hand-written BPTT (csrc/bptt_tc.cu): one ic3_bptt_step per lock-step iteration, last to first; no host
-        synchronisation.  Returns the device float64 vector of the three loss sums."""
+        """Hand-written BPTT (csrc/bptt_tc.cu): one ic3_bptt_step per lock-step iteration, last to first (one host read
+        up front: max |c| of the record, the bound behind the operand scale).  Returns the device float64 vector of the
+        three loss sums."""
         b, net, args, e = self._buf, self.policy_net, self.args, self.env.env
         lib = _lib.load()
         T, B, N, H = b['T'], e.nenvs, args.nagents, args.hid_size
