@@ -656,10 +656,12 @@ def e2e_loop(a, env, net, steps, np, torch, select_action):
     e = env.env
     e.strict = False
     pin = lambda *s, dtype: torch.empty(*s, dtype=dtype).pin_memory()
-    act_h, rew_h, done_h = pin(B, N, nh, dtype=torch.int32), pin(B, N, dtype=torch.float32), pin(B, dtype=torch.bool)
+    from ic3net_b200.action_utils import translate_action
+    act_h = [pin(B, N, dtype=torch.int32) for _ in range(nh)]           # per-head host arrays, like translate_action's
+    rew_h, done_h = pin(B, N, dtype=torch.float32), pin(B, dtype=torch.bool)
     alive_h = pin(B, N, dtype=torch.uint8)
     comm_h = pin(B, N, dtype=torch.uint8)
-    env_act_h = pin(B, N, dtype=torch.int32)
+    ones_h = torch.ones(B, N, dtype=torch.uint8)
     h2d = d2h = 0
 
     phases = dict(policy_enqueue=0.0, wait_actions=0.0, env_enqueue=0.0, wait_reward=0.0)
@@ -669,18 +671,19 @@ def e2e_loop(a, env, net, steps, np, torch, select_action):
         t0 = time.perf_counter()
         action_out, value, hc = net([obs, hc], info)                     # comm_action / alive_mask: host -> device
         action = select_action(a, action_out)
-        act_h.copy_(action, non_blocking=True)                           # D2H (translate_action -> numpy)
+        heads_d, _actual = translate_action(a, env, action)              # per-head arrays (trainer.py:65-66)
+        for k in range(nh):
+            act_h[k].copy_(heads_d[k], non_blocking=True)                # D2H (the reference's .numpy())
         t1 = time.perf_counter()
         torch.cuda.synchronize()
         t2 = time.perf_counter()
-        env_act_h.copy_(act_h[..., 0])
-        obs, reward, done, info_env = env.step([env_act_h])              # H2D actions
+        obs, reward, done, info_env = env.step(act_h)                    # H2D actions (the wrapper passes head 0)
         rew_h.copy_(reward, non_blocking=True)                           # D2H
         done_h.copy_(done, non_blocking=True)
         t3 = time.perf_counter()
         nxt = {}
         if a.hard_attn:
-            comm_h.copy_(act_h[..., -1] if not a.comm_action_one else torch.ones(B, N, dtype=torch.uint8))
+            comm_h.copy_(act_h[-1] if not a.comm_action_one else ones_h)    # trainer.py:55-58, on the host
             nxt["comm_action"] = comm_h
         if is_tj:
             alive_h.copy_(info_env["alive_mask"], non_blocking=True)     # D2H
@@ -691,8 +694,8 @@ def e2e_loop(a, env, net, steps, np, torch, select_action):
             for k, v in zip(("policy_enqueue", "wait_actions", "env_enqueue", "wait_reward"),
                             (t1 - t0, t2 - t1, t3 - t2, t4 - t3)):
                 phases[k] += v
-            h2d += env_act_h.numel() * 4 + (comm_h.numel() if a.hard_attn else 0) + (alive_h.numel() if is_tj else 0)
-            d2h += act_h.numel() * 4 + rew_h.numel() * 4 + done_h.numel() + (alive_h.numel() if is_tj else 0)
+            h2d += act_h[0].numel() * 4 + (comm_h.numel() if a.hard_attn else 0) + (alive_h.numel() if is_tj else 0)
+            d2h += nh * act_h[0].numel() * 4 + rew_h.numel() * 4 + done_h.numel() + (alive_h.numel() if is_tj else 0)
         if not is_tj and bool(done_h.any()):                             # finished PP envs start a new episode
             m = done_h.to(torch.uint8)
             e.reset(mask=m, want_obs=False)

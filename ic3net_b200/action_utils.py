@@ -33,6 +33,7 @@ def parse_action_args(args):
 
 
 _ticks = {}
+_cfgs = {}          # sampler launch descriptors by (B, N, heads, env_id0, seed)
 
 
 def _joined_view(action_out, heads):
@@ -67,11 +68,14 @@ def select_action(args, action_out, draws=None, tick=None):
     if logp is None:
         logp = torch.cat([a.to(torch.float32) for a in action_out], dim=-1).contiguous()
     B, N = logp.shape[0], logp.shape[1]
-    hd = (C.c_int32 * _lib.MAX_HEADS)(*(heads + [0] * (_lib.MAX_HEADS - len(heads))))
-    cfg = _lib.PolicyCfg(B=B, N=N, H=32, O=1, nheads=len(heads), head_dim=hd, hard_attn=0, comm_avg=0,
-                         comm_mask_zero=0, env_id0=int(getattr(args, 'env_id0', 0)),
-                         seed=int(getattr(args, 'seed', 0)) & 0xFFFFFFFFFFFFFFFF)
-    d = None
+    ckey = (B, N, tuple(heads), int(getattr(args, 'env_id0', 0)), int(getattr(args, 'seed', 0)))
+    cfg = _cfgs.get(ckey)
+    if cfg is None:
+        hd = (C.c_int32 * _lib.MAX_HEADS)(*(heads + [0] * (_lib.MAX_HEADS - len(heads))))
+        cfg = _cfgs[ckey] = _lib.PolicyCfg(B=B, N=N, H=32, O=1, nheads=len(heads), head_dim=hd, hard_attn=0,
+                                           comm_avg=0, comm_mask_zero=0, env_id0=ckey[3],
+                                           seed=ckey[4] & 0xFFFFFFFFFFFFFFFF)
+    d, bump = None, False
     if draws is not None:
         d = torch.as_tensor(np.asarray(draws.cpu() if torch.is_tensor(draws) else draws, dtype=np.int64))
         d = d.to(logp.device, torch.int32).reshape(B, N, len(heads)).contiguous()
@@ -79,11 +83,12 @@ def select_action(args, action_out, draws=None, tick=None):
         key = id(args)
         if key not in _ticks or _ticks[key].shape[0] != B:
             _ticks[key] = torch.zeros(B, dtype=torch.int32, device=logp.device)
-        tick = _ticks[key].clone()
-        _ticks[key] += 1
+        tick, bump = _ticks[key], True
     action = torch.empty(B, N, len(heads), dtype=torch.int32, device=logp.device)
     _lib.check(_lib.load().ic3_sample_actions(C.byref(cfg), logp.data_ptr(), _lib.ptr(tick), _lib.ptr(d),
                                               action.data_ptr(), _lib.stream()))
+    if bump:
+        tick += 1                 # after the sampler on the same stream: the kernel read the old count
     return action
 
 

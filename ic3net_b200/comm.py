@@ -24,6 +24,8 @@ from .lazy_obs import LazyObs
 
 def _as_u8(v, B, N, device):
     """info['comm_action'] / info['alive_mask'] (numpy or tensor, [N] or [B,N]) -> uint8 [B,N]."""
+    if torch.is_tensor(v) and v.dtype == torch.uint8 and v.dim() == 2 and v.is_contiguous():
+        return v if v.is_cuda else v.to(device, non_blocking=True)     # the common case: one (async if pinned) copy
     if torch.is_tensor(v) and v.is_cuda:
         t = v if v.dtype == torch.uint8 else (v != 0).to(torch.uint8)
     else:       # host mask: normalise on the host, then ONE copy (asynchronous when the source is pinned)
@@ -112,6 +114,7 @@ class CommNetMLP(nn.Module):
                                env_id0=int(getattr(args, 'env_id0', 0)),
                                seed=int(getattr(args, 'seed', 0)) & 0xFFFFFFFFFFFFFFFF,
                                obs_off=0, obs_vocab=0, obs_ncount=0, **var)
+        self._plist = None
         self._packed = None
         self._packed_key = None
         # 'tc' = tcgen05 tensor-core path (csrc/policy_tc.cu: hid_size 128, LSTM cell, one comm pass),
@@ -151,11 +154,24 @@ class CommNetMLP(nn.Module):
         return self._ws[B]
 
     def _param_list(self):
-        w = self._kernel_weights()
-        ps = []
-        for v in w.values():
-            ps += list(v) if isinstance(v, (list, tuple)) else [v]
-        return ps
+        """Flat list of the kernel-side tensors.  Cached: the Parameter OBJECTS of a module stay the same through
+        load_state_dict / optimizer steps / re-pointed ``.data`` (all seen by packed()'s data_ptr + version key);
+        ``_apply`` (``.to`` / ``.cuda`` / ``.float``) drops the cache, and code that assigns a NEW Parameter object
+        to a submodule calls ``invalidate_packed()``."""
+        if self._plist is None:
+            ps = []
+            for v in self._kernel_weights().values():
+                ps += list(v) if isinstance(v, (list, tuple)) else [v]
+            self._plist = ps
+        return self._plist
+
+    def invalidate_packed(self):
+        self._plist = None
+        self._packed_key = None
+
+    def _apply(self, fn, *a, **kw):
+        self.__dict__['_plist'] = None
+        return super(CommNetMLP, self)._apply(fn, *a, **kw)
 
     def packed(self):
         """K-major kernel layout of the parameters; re-packed (one kernel) when any parameter changed."""
