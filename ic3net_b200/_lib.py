@@ -32,7 +32,8 @@ _p = C.c_void_p
 
 class PPCfg(C.Structure):
     _fields_ = [("B", C.c_int32), ("N", C.c_int32), ("dim", C.c_int32), ("vision", C.c_int32),
-                ("mode", C.c_int32), ("naction", C.c_int32), ("env_id0", C.c_uint32), ("seed", C.c_uint64)]
+                ("mode", C.c_int32), ("naction", C.c_int32), ("env_id0", C.c_uint32), ("enemy_comm", C.c_int32),
+                ("seed", C.c_uint64)]
 
 
 class PPState(C.Structure):

@@ -7,6 +7,9 @@
 
 #define IC3_FULL_MASK 0xffffffffu
 
+// predator-prey: agent rows per environment (the prey is row N with --enemy_comm, predator_prey_env.py:203-207)
+__host__ __device__ __forceinline__ int ic3_pp_agents(const ic3_pp_cfg& c) { return c.N + (c.enemy_comm != 0 ? 1 : 0); }
+
 extern unsigned long long g_ic3_launches;  // c_api.cu
 
 #define IC3_LAUNCH_CHECK()                         \

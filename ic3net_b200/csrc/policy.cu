@@ -461,8 +461,9 @@ __global__ void __launch_bounds__(256) pp_encoder_index_kernel(ic3_pp_cfg env, i
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int row = blockIdx.x * (blockDim.x >> 5) + warp;
   const int N = env.N, D = env.dim, v = env.vision, W = 2 * v + 1, V = D * D + 4;
-  if (row >= env.B * N) return;
-  const int e = row / N, i = row - e * N;
+  const int NA = ic3_pp_agents(env);          // agent rows per env: row N = the prey (enemy_comm)
+  if (row >= env.B * NA) return;
+  const int e = row / NA, i = row - e * NA;
   int lr = -1, lc = -1;
   if (lane <= N) {
     const int* l = st.loc + ((size_t)e * (N + 1) + lane) * 2;
@@ -800,7 +801,7 @@ extern "C" int ic3_pp_encoder_index(const ic3_pp_cfg* env, const ic3_pp_state* s
   rc = packed_check(w);
   if (rc) return rc;
   if (!env || !st || !st->loc || !x) return IC3_E_NULL;
-  if (env->B != cfg->B || env->N != cfg->N || env->N >= IC3_MAX_AGENTS) return IC3_E_RANGE;
+  if (env->B != cfg->B || ic3_pp_agents(*env) != cfg->N || env->N >= IC3_MAX_AGENTS) return IC3_E_RANGE;
   const int W = 2 * env->vision + 1;
   if (cfg->O != W * W * (env->dim * env->dim + 4)) return IC3_E_RANGE;
   rc = ic3_pp_layout_check(env, cfg);

@@ -216,7 +216,7 @@ int ic3_tc_policy_step(const ic3_policy_cfg* cfg, const ic3_policy_packed* w, co
     IC3_LAUNCH_RC(ic3_launch_pdl(prep_kernel<XSRC_TENSOR, false>, dim3(2 * ntiles_pad), dim3(PREP_THREADS), prep_T_bytes(cfg->N), s, *cfg, *io, img, src, PrepBwd{}));
   } else if (io->pp_env && io->pp_state) {       // fused index encoder, predator-prey
     const int W = 2 * io->pp_env->vision + 1;
-    if (W * W > PREP_MAX_WW || io->pp_env->B != cfg->B || io->pp_env->N != cfg->N) return IC3_E_RANGE;
+    if (W * W > PREP_MAX_WW || io->pp_env->B != cfg->B || ic3_pp_agents(*io->pp_env) != cfg->N) return IC3_E_RANGE;
     if (cfg->O != W * W * (io->pp_env->dim * io->pp_env->dim + 4)) return IC3_E_RANGE;
     src.pp = *io->pp_env;
     src.pps = *io->pp_state;

@@ -191,18 +191,19 @@ __global__ void __launch_bounds__(256) prep_kernel(ic3_policy_cfg cfg, ic3_polic
   }
   if (XSRC == XSRC_PP) {          // predator_prey_env.py:188-210
     const int D = src.pp.dim, v = src.pp.vision, W = 2 * v + 1, WW = W * W, V = D * D + 4;
+    const int NP = src.pp.N;      // predators; agent row NP (present with enemy_comm: N == NP + 1) is the prey
     for (int p = threadIdx.x; p < PREP_ROWS * WW; p += blockDim.x) {
       const int rl = p / WW, w = p - rl * WW, row = row0 + rl;
       int feat = 0, cnt = 0;
       if (row < R) {
         const int e = row / N, i = row - e * N;
-        const int* l = src.pps.loc + (size_t)e * (N + 1) * 2;
+        const int* l = src.pps.loc + (size_t)e * (NP + 1) * 2;
         const int dy = w / W, dx = w - dy * W;
         const int rr = l[2 * i] - v + dy, cc = l[2 * i + 1] - v + dx;
         if (rr >= 0 && rr < D && cc >= 0 && cc < D) {
           int npred = 0;
-          for (int j = 0; j < N; ++j) npred += (l[2 * j] == rr && l[2 * j + 1] == cc);
-          const int nprey = (l[2 * N] == rr && l[2 * N + 1] == cc);
+          for (int j = 0; j < NP; ++j) npred += (l[2 * j] == rr && l[2 * j + 1] == cc);
+          const int nprey = (l[2 * NP] == rr && l[2 * NP + 1] == cc);
           feat = w * V + rr * D + cc;
           cnt = npred | (nprey << 8);
         } else {

@@ -1,7 +1,7 @@
 // Predator-prey environment kernels (reference: ic3net_envs/predator_prey_env.py).
 //
 // Layout in HBM: loc [B, N+1, 2] int32 (predators, then the prey), reached [B,N] u8,
-// done [B] u8.  One CTA per environment; warp 0 owns the integer state (lane = agent,
+// done [B] u8.  With cfg.enemy_comm the prey is agent row N of act / reward / obs (NA = N + 1 rows per env).  One CTA per environment; warp 0 owns the integer state (lane = agent,
 // reductions are ballots), all warps stream the observation block of the env:
 // [N * W*W cells][V] floats, contiguous, written once with 16-byte evict-first stores.
 #include <cstring>
@@ -64,7 +64,7 @@ __device__ __forceinline__ void pp_write_obs(const ic3_pp_cfg& cfg, const int* s
                                             uint32_t* s_cell, float* __restrict__ obs_env, bool keep) {
   const int N = cfg.N, D = cfg.dim, v = cfg.vision, W = 2 * v + 1, WW = W * W;
   const int V = D * D + 4, OUTSIDE = D * D + 1;
-  const int ncell = N * WW;
+  const int ncell = ic3_pp_agents(cfg) * WW;      // row N (enemy_comm): the window around the prey (:203-207)
   for (int c = threadIdx.x; c < ncell; c += blockDim.x) {
     const int i = c / WW, w = c - i * WW, dy = w / W, dx = w - dy * W;
     const int rr = s_r[i] - v + dy, cc = s_c[i] - v + dx;
@@ -122,6 +122,7 @@ __global__ void pp_step_kernel(PPArgs a, const int32_t* __restrict__ act, int ac
   __shared__ int s_r[IC3_MAX_AGENTS + 1], s_c[IC3_MAX_AGENTS + 1];
   const int e = blockIdx.x;
   const int N = a.cfg.N, D = a.cfg.dim;
+  const int NA = ic3_pp_agents(a.cfg);      // agent rows (N predators [+ the prey with enemy_comm])
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp == 0) {
     int rr = 0, cc = 0, rch = 0;
@@ -131,17 +132,17 @@ __global__ void pp_step_kernel(PPArgs a, const int32_t* __restrict__ act, int ac
       cc = l[1];
     }
     if (lane < N) rch = a.st.reached[(size_t)e * N + lane];
-    if (do_step && r.has && ic3_rollout_halted(r.io, e, a.cfg.B, N, lane)) {
+    if (do_step && r.has && ic3_rollout_halted(r.io, e, a.cfg.B, NA, lane)) {
       // this slot has completed its batch (trainer.py:231): nothing moves, null records
     } else if (do_step) {
       if (a.st.done[e]) {  // :129-130 RuntimeError("Episode is done")
         if (lane == 0) atomicOr(err, IC3_ERR_EPISODE_DONE);
       } else {
         int av = 4;
-        if (r.has && r.io.head_partial) av = ic3_rollout_heads(r.io, a.cfg.seed, a.cfg.env_id0, a.st.tick, e, N, lane);
-        else if (lane < N) av = act[((size_t)e * N + lane) * act_stride];
-        if (lane >= N) av = 4;
-        if (lane < N && (av < 0 || av > a.cfg.naction)) atomicOr(err, IC3_ERR_BAD_ACTION);  // :137 (sic, <=)
+        if (r.has && r.io.head_partial) av = ic3_rollout_heads(r.io, a.cfg.seed, a.cfg.env_id0, a.st.tick, e, NA, lane);
+        else if (lane < NA) av = act[((size_t)e * NA + lane) * act_stride];
+        if (lane >= NA) av = 4;
+        if (lane < NA && (av < 0 || av > a.cfg.naction)) atomicOr(err, IC3_ERR_BAD_ACTION);  // :137 (sic, <=)
         if (lane < N && !rch) {  // _take_action :212-252: every move is a clamped move
           if (av == 0) rr = max(0, rr - 1);
           else if (av == 1) cc = min(D - 1, cc + 1);
@@ -158,6 +159,7 @@ __global__ void pp_step_kernel(PPArgs a, const int32_t* __restrict__ act, int ac
           else if (a.cfg.mode == IC3_PP_COMPETITIVE) rew = 0.05 / (double)n_on;  // :264-266
           else rew = 0.0;                                                         // :267-268 PREY_REWARD
         }
+        if (lane == N) rew = n_on == 0 ? 0.05 : 0.0;   // prey reward (enemy_comm row), :276-281
         rch |= on ? 1 : 0;  // :271
         const bool allr = __ballot_sync(IC3_FULL_MASK, lane >= N || rch) == IC3_FULL_MASK;
         const bool done = (a.cfg.mode == IC3_PP_MIXED) && allr;  // :273-274
@@ -168,15 +170,15 @@ __global__ void pp_step_kernel(PPArgs a, const int32_t* __restrict__ act, int ac
           l[0] = rr;
           l[1] = cc;
           a.st.reached[(size_t)e * N + lane] = (uint8_t)rch;
-          reward[(size_t)e * N + lane] = (float)rew;
         }
+        if (lane < NA) reward[(size_t)e * NA + lane] = (float)rew;
         if (lane == 0) {
           a.st.done[e] = done ? 1 : 0;
           a.st.success[e] = success;
           a.st.tick[e] += 1;
         }
         if (r.has) {
-          const bool done_t = ic3_rollout_tail(r.io, e, a.cfg.B, N, lane, (float)rew, done, 1, 0, success);
+          const bool done_t = ic3_rollout_tail(r.io, e, a.cfg.B, NA, lane, (float)rew, done, 1, 0, success);
           if (done_t) {
             __syncwarp();
             pp_reset_env(a, e, lane);
@@ -192,7 +194,7 @@ __global__ void pp_step_kernel(PPArgs a, const int32_t* __restrict__ act, int ac
     }
     if (do_step && r.has && r.io.snap_T > 0) {          // inputs of the next policy step, for compute_grad
       __syncwarp();
-      ic3_rollout_snapshot(r.io, e, a.cfg.B, N, lane);
+      ic3_rollout_snapshot(r.io, e, a.cfg.B, NA, lane);
       if (r.io.snap_pp_loc && r.io.t + 1 < r.io.snap_T && lane <= N) {
         int* d = r.io.snap_pp_loc + (((size_t)(r.io.t + 1) * a.cfg.B + e) * (N + 1) + lane) * 2;
         d[0] = rr;
@@ -207,7 +209,7 @@ __global__ void pp_step_kernel(PPArgs a, const int32_t* __restrict__ act, int ac
   if (obs == nullptr) return;
   __syncthreads();
   const int W = 2 * a.cfg.vision + 1;
-  pp_write_obs<VEC4>(a.cfg, s_r, s_c, s_cell, obs + (size_t)e * N * W * W * (D * D + 4), keep_l2 != 0);
+  pp_write_obs<VEC4>(a.cfg, s_r, s_c, s_cell, obs + (size_t)e * NA * W * W * (D * D + 4), keep_l2 != 0);
 }
 
 int pp_check(const ic3_pp_cfg* cfg, const ic3_pp_state* st) {
@@ -227,12 +229,13 @@ int pp_launch(const ic3_pp_cfg* cfg, const ic3_pp_state* st, const int32_t* act,
   PPArgs a{*cfg, *st};
   const int W = 2 * cfg->vision + 1;
   const int V = cfg->dim * cfg->dim + 4;
-  const size_t smem = obs ? (size_t)cfg->N * W * W * sizeof(uint32_t) : 0;
+  const int NA = ic3_pp_agents(*cfg);
+  const size_t smem = obs ? (size_t)NA * W * W * sizeof(uint32_t) : 0;
   const int threads = obs ? 256 : 32;
   const bool vec4 = (V % 4 == 0) && ((reinterpret_cast<uintptr_t>(obs) & 15) == 0);
   RolloutOpt ro = make_rollout_opt(r);
   // small observation batches stay in L2 for the encoder that follows (see IC3_OBS_L2_KEEP_BYTES)
-  const int keep = obs && (size_t)cfg->B * cfg->N * W * W * V * sizeof(float) <= IC3_OBS_L2_KEEP_BYTES;
+  const int keep = obs && (size_t)cfg->B * NA * W * W * V * sizeof(float) <= IC3_OBS_L2_KEEP_BYTES;
   if (vec4)
     IC3_LAUNCH_RC(ic3_launch_pdl(pp_step_kernel<true>, dim3(cfg->B), dim3(threads), smem, s, a, act, act_stride, reward, obs,
                                  err, ro, do_step, keep));

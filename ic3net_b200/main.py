@@ -100,8 +100,11 @@ def derive_args(args):
         if args.env_name == "traffic_junction":
             args.comm_action_one = True
     args.nfriendly = args.nagents
-    if getattr(args, 'enemy_comm', False):
-        raise NotImplementedError("enemy_comm is outside the accelerated path")
+    if getattr(args, 'enemy_comm', False):       # main.py:126-130: the enemies become agents of the policy
+        if hasattr(args, 'nenemies'):
+            args.nagents += args.nenemies
+        else:
+            raise RuntimeError("Env. needs to pass argument 'nenemy'.")
     if args.plot or args.display:
         raise NotImplementedError("--plot / --display (visdom, curses) are outside the accelerated path")
     return args

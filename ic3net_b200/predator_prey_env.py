@@ -7,7 +7,8 @@ Same surface as the reference ``ic3net_envs/predator_prey_env.py:PredatorPreyEnv
 ``args.nenvs`` independent environments whose state lives in HBM and is advanced
 by the CUDA kernels in csrc/pp_env.cu.  Returned arrays are CUDA tensors with a
 leading env dimension: obs ``[B, N, W, W, V]`` float32, reward ``[B, N]`` float32,
-done ``[B]`` bool; info holds live views of the state like the reference does.
+done ``[B]`` bool; info holds live views of the state like the reference does.  With
+``--enemy_comm`` the prey is one more agent row (N + 1 rows of obs / reward / action).
 """
 import ctypes as C
 
@@ -55,8 +56,8 @@ class PredatorPreyEnv(object):
         self.stay = not args.no_stay
         if args.moving_prey:
             raise NotImplementedError           # predator_prey_env.py:84-85
-        if self.enemy_comm or self.nprey != 1:
-            raise NotImplementedError("enemy_comm / nenemies != 1 are outside the accelerated path")
+        if self.nprey != 1:
+            raise NotImplementedError("nenemies != 1: the reference reward logic only works for one prey (:258)")
         if self.mode not in _lib.PP_MODES:       # :269
             raise RuntimeError("Incorrect mode, Available modes: [cooperative|competitive|mixed]")
         self.naction = 5 if self.stay else 4
@@ -69,11 +70,13 @@ class PredatorPreyEnv(object):
 
         self.nenvs = B = int(getattr(args, 'nenvs', 1))
         N = self.npredator
+        # --enemy_comm (:203-207, :255, :276-281): the prey is agent row N of obs / reward / action (action ignored)
+        self.nagent_rows = NA = N + (1 if self.enemy_comm else 0)
         self.device = torch.device('cuda', torch.cuda.current_device())
         seed = int(getattr(args, 'seed', 0))
         self.cfg = _lib.PPCfg(B=B, N=N, dim=self.dim, vision=self.vision, mode=_lib.PP_MODES[self.mode],
                               naction=self.naction, env_id0=int(getattr(args, 'env_id0', 0)),
-                              seed=seed & 0xFFFFFFFFFFFFFFFF)
+                              enemy_comm=int(bool(self.enemy_comm)), seed=seed & 0xFFFFFFFFFFFFFFFF)
         dev = self.device
         self.loc = torch.zeros(B, N + 1, 2, dtype=torch.int32, device=dev)
         self.reached_prey = torch.zeros(B, N, dtype=torch.uint8, device=dev)
@@ -85,7 +88,7 @@ class PredatorPreyEnv(object):
         self.state = _lib.PPState(loc=self.loc.data_ptr(), reached=self.reached_prey.data_ptr(),
                                   done=self.done.data_ptr(), success=self.success.data_ptr(),
                                   episode=self.episode.data_ptr(), tick=self.tick.data_ptr())
-        self.obs_shape = (B, N, W, W, self.vocab_size)
+        self.obs_shape = (B, NA, W, W, self.vocab_size)
         self.obs_dim = W * W * self.vocab_size
         # encoder layout hint (ic3_policy_cfg.obs_off / obs_vocab / obs_ncount): cells of V entries, last two = counts
         self.obs_layout = (0, self.vocab_size, 2)
@@ -159,7 +162,7 @@ class PredatorPreyEnv(object):
 
     def _as_action(self, action):
         a = action if torch.is_tensor(action) else torch.as_tensor(np.asarray(action))
-        a = a.to(self.device, torch.int32, non_blocking=True).reshape(self.nenvs, self.npredator).contiguous()
+        a = a.to(self.device, torch.int32, non_blocking=True).reshape(self.nenvs, self.nagent_rows).contiguous()
         return a
 
     def check_errors(self):
@@ -173,7 +176,7 @@ class PredatorPreyEnv(object):
 
     def step(self, action, obs_out=None):
         act = self._as_action(action)
-        reward = torch.empty(self.nenvs, self.npredator, dtype=torch.float32, device=self.device)
+        reward = torch.empty(self.nenvs, self.nagent_rows, dtype=torch.float32, device=self.device)
         lazy = obs_out is None and self.obs_api == 'handle'
         obs = None if lazy else (self._new_obs() if obs_out is None else obs_out)
         self.obs_version += 1
@@ -192,7 +195,7 @@ class PredatorPreyEnv(object):
     def reward_terminal(self):
         # the reference re-runs _get_reward here (side effects only, idempotent on an
         # unchanged state) and returns zeros (:292-293)
-        return torch.zeros(self.nenvs, self.npredator, dtype=torch.float32, device=self.device)
+        return torch.zeros(self.nenvs, self.nagent_rows, dtype=torch.float32, device=self.device)
 
     def get_stat(self):
         """stat['success'] summed over the envs of the batch (host read)."""

@@ -174,7 +174,7 @@ class Trainer(object):
                 b.update(s_tjloc=z(T, B, N, 2, dtype=torch.int32), s_tjalive=z(T, B, N, dtype=torch.uint8),
                          s_tjlast=z(T, B, N, dtype=torch.uint8), s_tjroute=z(T, B, N, dtype=torch.int32))
             else:
-                b['s_loc'] = z(T, B, N + 1, 2, dtype=torch.int32)
+                b['s_loc'] = z(T, B, e.npredator + 1, 2, dtype=torch.int32)    # predators + the prey
         elif self.record_for_grad:
             # inputs of every policy step + (h, c) checkpoints at the window starts
             W = self.grad_window
@@ -185,7 +185,7 @@ class Trainer(object):
             if self.is_tj:
                 b['s_obs'] = z(T, B, N, self.env.observation_dim)
             else:
-                b['s_loc'] = z(T, B, N + 1, 2, dtype=torch.int32)
+                b['s_loc'] = z(T, B, e.npredator + 1, 2, dtype=torch.int32)    # predators + the prey
         self._buf = b
         self._graph = None
         return b
@@ -406,9 +406,15 @@ class Trainer(object):
         stat['num_episodes'] = int(round(float(v[0])))
         stat['num_steps'] = int(round(float(v[1])))
         stat['steps_taken'] = stat['num_steps']
-        stat['reward'] = v[4:4 + N].copy()
+        nf = int(getattr(args, 'nfriendly', N))                 # trainer.py:73-75,86-88: friendly / enemy split
+        enemy = bool(getattr(args, 'enemy_comm', False))
+        stat['reward'] = v[4:4 + nf].copy()
+        if enemy:
+            stat['enemy_reward'] = v[4 + nf:4 + N].copy()
         if args.hard_attn and args.commnet:
-            stat['comm_action'] = v[4 + N:4 + 2 * N].copy()
+            stat['comm_action'] = v[4 + N:4 + N + nf].copy()
+            if enemy:
+                stat['enemy_comm'] = v[4 + N + nf:4 + 2 * N].copy()
         if not (not self.is_tj and args.mode == 'competitive'):
             stat['success'] = int(round(float(v[2])))
         if self.is_tj:
@@ -456,13 +462,14 @@ class Trainer(object):
         [R, 3*W*W] from a state snapshot loc [B, N+1, 2]."""
         e = self.env.env
         D, v, N = e.dim, e.vision, e.npredator
+        NA = e.nagent_rows                                                   # + the prey's own row with enemy_comm
         W, V = 2 * v + 1, e.vocab_size
         loc = loc.long()
         pr, pc = loc[:, :N, 0], loc[:, :N, 1]
         ar = torch.arange(W, device=loc.device)
         dy, dx = ar.repeat_interleave(W), ar.repeat(W)                       # window cell w = dy*W + dx
-        rr = pr.unsqueeze(-1) - v + dy                                       # [B, N, W*W]
-        cc = pc.unsqueeze(-1) - v + dx
+        rr = loc[:, :NA, 0].unsqueeze(-1) - v + dy                           # [B, NA, W*W]
+        cc = loc[:, :NA, 1].unsqueeze(-1) - v + dx
         inside = (rr >= 0) & (rr < D) & (cc >= 0) & (cc < D)
         base = torch.arange(W * W, device=loc.device) * V
         cls = torch.where(inside, rr * D + cc, torch.full_like(rr, D * D + 1)) + base

@@ -68,12 +68,16 @@ uint64_t ic3_launch_count(void);
  * ---------------------------------------------------------------------- */
 typedef struct {
   int32_t B;        /* environments in the batch */
-  int32_t N;        /* predators (args.nfriendly, :79) ; one fixed prey (:78) */
+  int32_t N;        /* predators (args.nfriendly, :79) ; one fixed prey (:78).  Rows of act / reward / obs per env:
+                       N + (enemy_comm != 0) */
   int32_t dim;      /* board is dim x dim (:80) */
   int32_t vision;   /* window is (2v+1)^2 (:107) */
   int32_t mode;     /* IC3_PP_* (:262-269) */
   int32_t naction;  /* 5, or 4 with --no_stay (:88-92) */
   uint32_t env_id0; /* global id of env 0 (rank * B): RNG stream selector */
+  int32_t enemy_comm; /* --enemy_comm (:69, :203-207, :255, :276-281; main.py:124-131): the prey is one more agent of
+                         the policy -- row N of obs / reward / act (its action is ignored, :214-217; its reward is
+                         +0.05 while no predator stands on it, else 0) */
   uint64_t seed;
 } ic3_pp_cfg;
 

@@ -168,8 +168,8 @@ def save(name, meta, **arrays):
 
 def make_oracle_env(args, tables=None):
     if args.env_name == "predator_prey":
-        return pp_env.PredatorPreyOracle(args.nagents, args.dim, args.vision, args.mode,
-                                         args.nenemies, args.no_stay)
+        return pp_env.PredatorPreyOracle(args.nfriendly, args.dim, args.vision, args.mode,
+                                         args.nenemies, args.no_stay, getattr(args, "enemy_comm", False))
     return tj_env.TrafficJunctionOracle(args.nagents, args.dim, args.vision, args.difficulty, tables,
                                         args.add_rate_min, args.add_rate_max, args.curr_start, args.curr_end)
 
@@ -437,13 +437,19 @@ def gen_episode_case(name, seed, env_ids, wseed, hsteps=(0, 1), epoch=0, **kw):
         ostat = dict(orc.stat)
         assert stat["num_steps"] == L
         assert stat.get("success") == ostat.get("success")
-        assert np.allclose(stat["reward"], np.sum(rec["reward"], 0))
+        nf = args.nfriendly                                   # trainer.py:73-75,86-88: friendly / enemy split
+        assert np.allclose(stat["reward"], np.sum(rec["reward"], 0)[:nf])
+        if getattr(args, "enemy_comm", False):
+            assert np.allclose(stat["enemy_reward"], np.sum(rec["reward"], 0)[nf:])
         ep = {k: np.array(v) for k, v in rec.items()}
         ep["h_sel"], ep["c_sel"] = np.array(hsel), np.array(csel)
         ep["h_steps"] = np.array([t for t in range(L) if t in hsteps or t == L - 1])
         ep["success"] = np.array(int(stat.get("success", -1)))
         if "comm_action" in stat:
             ep["stat_comm"] = np.asarray(stat["comm_action"], dtype=np.float64)
+        if "enemy_comm" in stat:
+            ep["stat_enemy_comm"] = np.asarray(stat["enemy_comm"], dtype=np.float64)
+            ep["stat_enemy_reward"] = np.asarray(stat["enemy_reward"], dtype=np.float64)
         eps.append(ep)
     meta = dict(kind="episode", seed=seed, env_ids=list(env_ids), weights_seed=wseed, epoch=epoch,
                 args={k: v for k, v in vars(args).items() if isinstance(v, (int, float, str, bool))},
@@ -705,6 +711,18 @@ def gen_variant_cases():
                      rnn_type="LSTM")
 
 
+def gen_enemy_comm_cases():
+    """--enemy_comm (predator_prey_env.py:203-207,255,276-281; main.py:124-131; trainer.py:73-75,86-88,120-121): the prey
+    is one more agent of the policy -- observation row, reward entry, communication; its action is ignored."""
+    gen_env_case("env_pp_enemy", 30, 16, 4, env_name="predator_prey", nagents=3, dim=4, vision=1, enemy_comm=True)
+    gen_env_case("env_pp_enemy_coop", 30, 17, 6, env_name="predator_prey", nagents=2, dim=3, vision=0, enemy_comm=True,
+                 mode="cooperative")
+    gen_episode_case("ep_pp_enemy_ic3net", 48, (0, 3), 58, hsteps=(0, 1, 8), env_name="predator_prey", nagents=3,
+                     dim=5, vision=1, max_steps=20, hid_size=128, ic3net=True, enemy_comm=True)
+    gen_grad_case("grad_pp_enemy_ic3net_h128", 68, 5, 78, env_name="predator_prey", nagents=3, dim=5, vision=1,
+                  max_steps=12, hid_size=128, ic3net=True, enemy_comm=True, batch_size=40, detach_gap=5)
+
+
 def gen_hid128_grad_cases():
     """Gradient fixtures at hid_size 128 (the shape the tensor-core rollout and the BPTT kernels run at) covering the
     loss / comm variants: entropy bonus, normalised advantages, cooperative returns, comm_mode sum, plain CommNet (no
@@ -725,6 +743,11 @@ def main():
         import warnings
         warnings.filterwarnings("ignore")
         gen_variant_cases()
+        return 0
+    if "--enemy-only" in sys.argv:
+        import warnings
+        warnings.filterwarnings("ignore")
+        gen_enemy_comm_cases()
         return 0
     if "--grad128-only" in sys.argv:
         import warnings
@@ -798,6 +821,7 @@ def main():
                   max_steps=20, hid_size=64, commnet=True, difficulty="easy", add_rate_min=0.3, add_rate_max=0.3,
                   batch_size=50, mean_ratio=0.5, gamma=0.9)
     gen_hid128_grad_cases()
+    gen_enemy_comm_cases()
     gen_variant_cases()
     gen_rmsprop_case("rmsprop_ref", 81)
     gen_log_case()

@@ -26,12 +26,16 @@ class PredatorPreyOracle(object):
     PREY_REWARD = 0.0          # :41
     POS_PREY_REWARD = 0.05     # :42
 
-    def __init__(self, nagents, dim, vision, mode="mixed", nenemies=1, no_stay=False):
+    def __init__(self, nagents, dim, vision, mode="mixed", nenemies=1, no_stay=False, enemy_comm=False):
+        """``nagents`` = predators (args.nfriendly).  ``enemy_comm``: the prey is one more AGENT of the policy -- it
+        gets an observation row (:203-207) and a reward entry (:255, :276-281), its action is ignored (:214-217)."""
         if nenemies != 1:
             raise NotImplementedError("reference reward logic only works for one prey (:258)")
         if mode not in MODES:
             raise RuntimeError("Incorrect mode, Available modes: [cooperative|competitive|mixed]")
         self.n, self.dim, self.vision, self.mode = int(nagents), int(dim), int(vision), mode
+        self.enemy_comm = bool(enemy_comm)
+        self.na = self.n + (1 if self.enemy_comm else 0)          # rows of obs / reward (:203-207, :255)
         self.naction = 4 if no_stay else 5                       # :88-92
         base = self.dim * self.dim                                # :96
         self.OUTSIDE, self.PREY, self.PREDATOR = base + 1, base + 2, base + 3   # :97-99
@@ -87,8 +91,9 @@ class PredatorPreyOracle(object):
         self.predator_loc[i] = (r, c)
 
     def _reward(self):
-        reward = np.full(self.n, self.TIMESTEP_PENALTY)
-        on = np.all(self.predator_loc == self.prey_loc[0], axis=1)     # :258
+        reward = np.full(self.na, self.TIMESTEP_PENALTY)                # :255-256
+        on = np.zeros(self.na, dtype=bool)
+        on[: self.n] = np.all(self.predator_loc == self.prey_loc[0], axis=1)     # :258
         n_on = int(on.sum())
         if self.mode == "cooperative":
             reward[on] = self.POS_PREY_REWARD * n_on
@@ -97,6 +102,8 @@ class PredatorPreyOracle(object):
                 reward[on] = self.POS_PREY_REWARD / n_on
         else:
             reward[on] = self.PREY_REWARD
+        on = on[: self.n]
+        reward[self.n:] = -1 * self.TIMESTEP_PENALTY if n_on == 0 else 0      # prey reward :276-281
         self.reached[on] = 1                                            # :271
         if self.mode == "mixed" and np.all(self.reached == 1):          # :273-274
             self.episode_over = True
@@ -123,15 +130,16 @@ class PredatorPreyOracle(object):
     # ---- observation -----------------------------------------------------------
     def get_obs(self):
         """[N, W, W, V] int64 exactly like :188-210 (counts, not booleans)."""
-        n, v, W, V, D = self.n, self.vision, self.W, self.vocab_size, self.dim
-        obs = np.zeros((n, W, W, V), dtype=np.int64)
+        v, W, V, D = self.vision, self.W, self.vocab_size, self.dim
+        obs = np.zeros((self.na, W, W, V), dtype=np.int64)
         pred_cnt = np.zeros((D, D), dtype=np.int64)
         prey_cnt = np.zeros((D, D), dtype=np.int64)
         for r, c in self.predator_loc:
             pred_cnt[r, c] += 1
         for r, c in self.prey_loc:
             prey_cnt[r, c] += 1
-        for i, (r, c) in enumerate(self.predator_loc):
+        rows = list(self.predator_loc) + (list(self.prey_loc) if self.enemy_comm else [])     # :198-207
+        for i, (r, c) in enumerate(rows):
             for dy in range(W):
                 for dx in range(W):
                     rr, cc = r - v + dy, c - v + dx
@@ -146,4 +154,4 @@ class PredatorPreyOracle(object):
     def flat_obs(self, obs=None):
         """env_wrappers.py:98-99: [N, O] float64."""
         obs = self.get_obs() if obs is None else obs
-        return obs.reshape(self.n, -1).astype(np.float64)
+        return obs.reshape(self.na, -1).astype(np.float64)

@@ -228,6 +228,8 @@ def make_args(**kw):
         if a.env_name == "traffic_junction":
             a.comm_action_one = True
     a.nfriendly = a.nagents
+    if getattr(a, "enemy_comm", False):          # main.py:124-131: the prey becomes one more agent of the policy
+        a.nagents += a.nenemies
     return a
 
 

@@ -57,6 +57,7 @@ def finish_args(args, env):
 def make_oracle_env(args, tables=None):
     from oracle import pp_env, tj_env
     if args.env_name == "predator_prey":
-        return pp_env.PredatorPreyOracle(args.nagents, args.dim, args.vision, args.mode, args.nenemies, args.no_stay)
+        return pp_env.PredatorPreyOracle(args.nfriendly, args.dim, args.vision, args.mode, args.nenemies, args.no_stay,
+                                         getattr(args, "enemy_comm", False))
     return tj_env.TrafficJunctionOracle(args.nagents, args.dim, args.vision, args.difficulty, tables,
                                         args.add_rate_min, args.add_rate_max, args.curr_start, args.curr_end)

@@ -121,15 +121,17 @@ def test_sparse_observation_path_equals_dense():
         assert torch.allclose(Gd[key], Gs[key], rtol=1e-11, atol=1e-13), key
 
 
+@pytest.mark.parametrize("enemy", [False, True])
 @pytest.mark.parametrize("dim,vision,n", [(5, 0, 3), (4, 1, 2), (6, 2, 5), (20, 1, 10)])
-def test_sparse_pp_observation_equals_oracle_observation(dim, vision, n):
+def test_sparse_pp_observation_equals_oracle_observation(dim, vision, n, enemy):
     """Trainer._pp_sparse_obs (the (index, value) form of the predator-prey observation both gradient paths consume)
     scattered back to dense equals the oracle's observation, incl. stacked predators, prey under a predator and
     windows that leave the grid.  Runs on CPU: the method only touches torch ops and four env attributes."""
     from types import SimpleNamespace
     from oracle.pp_env import PredatorPreyOracle
     from ic3net_b200.trainer import Trainer
-    orc = PredatorPreyOracle(n, dim, vision)
+    orc = PredatorPreyOracle(n, dim, vision, enemy_comm=enemy)      # enemy_comm: the prey's own row comes last
+    na = n + int(enemy)
     rs = np.random.RandomState(dim * 10 + vision)
     B = 6
     loc = rs.randint(0, dim, size=(B, n + 1, 2))
@@ -138,14 +140,14 @@ def test_sparse_pp_observation_equals_oracle_observation(dim, vision, n):
     loc[2, 0] = (0, 0)                         # window leaves the grid (vision > 0)
     loc[3, :] = (dim - 1, dim - 1)             # everybody in one corner
     fake = SimpleNamespace(env=SimpleNamespace(env=SimpleNamespace(dim=dim, vision=vision, npredator=n,
-                                                                   vocab_size=orc.vocab_size)))
+                                                                   nagent_rows=na, vocab_size=orc.vocab_size)))
     idx, val = Trainer._pp_sparse_obs(fake, torch.tensor(loc, dtype=torch.int32))
     O = orc.obs_dim
-    dense = torch.zeros(B * n, O, dtype=torch.float64)
+    dense = torch.zeros(B * na, O, dtype=torch.float64)
     dense.scatter_add_(1, idx, val.double())
     for b in range(B):
         orc.reset(locs=loc[b])
-        assert np.array_equal(dense[b * n:(b + 1) * n].numpy(), orc.flat_obs()), b
+        assert np.array_equal(dense[b * na:(b + 1) * na].numpy(), orc.flat_obs()), b
     # and through the encoder of bptt.py: sparse form == dense form
     P = {"encoder.weight": torch.randn(7, O, dtype=torch.float64), "encoder.bias": torch.randn(7, dtype=torch.float64)}
     assert torch.allclose(bptt.encode(P, (idx, val.double())), bptt.encode(P, dense), rtol=1e-12, atol=1e-12)

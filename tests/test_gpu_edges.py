@@ -116,6 +116,13 @@ def test_cli_runs_reference_flags(capsys):
              "--hid_size", "64", "--num_epochs", "1", "--epoch_size", "1", "--batch_size", "10", "--seed", "2"]
     assert cli.main(small) == 0
     assert cli.main(small + ["--recurrent", "--mean_ratio", "0"]) == 0
+    # --enemy_comm (main.py:124-131): the prey joins the policy; its reward / gate statistics print on their own lines
+    capsys.readouterr()
+    rc = cli.main(["--env_name", "predator_prey", "--nagents", "3", "--dim", "5", "--vision", "1", "--max_steps", "10",
+                   "--hid_size", "128", "--ic3net", "--recurrent", "--enemy_comm", "--nenvs", "16", "--num_epochs", "1",
+                   "--epoch_size", "2", "--batch_size", "10", "--seed", "3"])
+    out = capsys.readouterr().out
+    assert rc == 0 and "Enemy-Reward: [" in out and "Enemy-Comm: [" in out
     rc = cli.main(["--env_name", "traffic_junction", "--nagents", "5", "--dim", "6", "--vision", "0", "--max_steps",
                    "20", "--hid_size", "128", "--ic3net", "--recurrent", "--nenvs", "32", "--num_epochs", "1",
                    "--epoch_size", "1", "--batch_size", "20", "--seed", "4", "--difficulty", "easy", "--add_rate_min",

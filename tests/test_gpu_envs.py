@@ -55,7 +55,7 @@ def test_env_matches_reference_golden(name):
 
 
 @pytest.mark.parametrize("name", ["env_pp_easy", "env_pp_v1", "env_pp_hard", "env_tj_medium", "env_tj_hard_v1",
-                                  "env_tj_easy"])
+                                  "env_tj_easy", "env_pp_enemy", "env_pp_enemy_coop"])
 def test_batched_envs_match_oracle(name):
     """B = 37 envs with distinct Philox streams vs 37 oracle instances, random actions."""
     meta, z = load_golden(name)

@@ -71,7 +71,7 @@ def test_first_episode_matches_reference_golden(name, obs_mode, impl):
 
 @pytest.mark.parametrize("name,B,T", [("ep_pp_easy_ic3net", 11, 70), ("ep_tj_medium_ic3net", 7, 80),
                                       ("ep_tj_easy_ic3net", 9, 45), ("ep_pp_hard_commnet", 3, 90),
-                                      ("ep_tj_medium_v1_commnet", 4, 50)])
+                                      ("ep_tj_medium_v1_commnet", 4, 50), ("ep_pp_enemy_ic3net", 9, 50)])
 @pytest.mark.parametrize("impl", ["tc", "simt"])
 def test_lockstep_rollout_matches_oracle(name, B, T, impl):
     """Every slot, every episode (auto-reset, cut at the batch end), teacher-forced with
@@ -116,10 +116,16 @@ def test_lockstep_rollout_matches_oracle(name, B, T, impl):
             k += 1
     assert tot["flips"] <= 1e-3 * tot["draws"]
     assert stat["num_steps"] == B * T and stat["num_episodes"] == tot["episodes"]
-    assert np.allclose(stat["reward"], tot["reward"], rtol=1e-5, atol=1e-4)
+    nf = args.nfriendly                   # with --enemy_comm the prey's entries are reported apart (trainer.py:73-75,86-88)
+    assert np.allclose(stat["reward"], tot["reward"][:nf], rtol=1e-5, atol=1e-4)
     assert stat["success"] == tot["success"]
     if args.hard_attn:
-        assert np.array_equal(stat["comm_action"], tot["comm"])
+        assert np.array_equal(stat["comm_action"], tot["comm"][:nf])
+    if getattr(args, "enemy_comm", False):
+        assert np.allclose(stat["enemy_reward"], tot["reward"][nf:], rtol=1e-5, atol=1e-4)
+        assert np.array_equal(stat["enemy_comm"], tot["comm"][nf:])
+    else:
+        assert "enemy_reward" not in stat and "enemy_comm" not in stat
 
 
 def test_graph_replay_equals_eager():
