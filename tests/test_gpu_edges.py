@@ -70,6 +70,12 @@ def test_thirty_one_predators_and_one_env():
     rollout_vs_oracle(pp_args(31, 8, 1, 1), 14)                # lane 31 holds the prey; B = 1
 
 
+def test_thirty_one_predators_and_a_communicating_prey():
+    # --enemy_comm at the lane limit: 31 predators + the prey = 32 agent rows of the policy, prey on lane 31
+    stat = rollout_vs_oracle(pp_args(32, 8, 1, 2, nfriendly=31, enemy_comm=True), 14)
+    assert len(stat["reward"]) == 31 and len(stat["enemy_reward"]) == 1 and len(stat["enemy_comm"]) == 1
+
+
 def test_thirty_two_cars():
     meta, z = load_golden("env_tj_hard")
     a = ns(meta["args"], nagents=32, nfriendly=32, nenvs=3, seed=2, env_id0=0, hid_size=128, recurrent=True,
