@@ -6,6 +6,7 @@
 #include "../../include/ic3net_b200.h"
 
 #define IC3_FULL_MASK 0xffffffffu
+#define IC3_ENV_WARPS 8      // envs per CTA of an env step launched without an observation block (warp = env)
 
 // predator-prey: agent rows per environment (the prey is row N with --enemy_comm, predator_prey_env.py:203-207)
 __host__ __device__ __forceinline__ int ic3_pp_agents(const ic3_pp_cfg& c) { return c.N + (c.enemy_comm != 0 ? 1 : 0); }

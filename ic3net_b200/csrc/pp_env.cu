@@ -120,11 +120,13 @@ __global__ void pp_step_kernel(PPArgs a, const int32_t* __restrict__ act, int ac
   ic3_pdl_wait();      // everything below reads state / actions written by the previous kernel of the step
   extern __shared__ uint32_t s_cell[];
   __shared__ int s_r[IC3_MAX_AGENTS + 1], s_c[IC3_MAX_AGENTS + 1];
-  const int e = blockIdx.x;
   const int N = a.cfg.N, D = a.cfg.dim;
   const int NA = ic3_pp_agents(a.cfg);      // agent rows (N predators [+ the prey with enemy_comm])
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (warp == 0) {
+  // with an observation block to write: one CTA per env, warp 0 owns the state.  Without (index-form encoder /
+  // observation handles): the state update is all there is, one WARP per env, several envs per CTA
+  const int e = obs ? (int)blockIdx.x : (int)(blockIdx.x * (blockDim.x >> 5)) + warp;
+  if (obs ? warp == 0 : e < a.cfg.B) {
     int rr = 0, cc = 0, rch = 0;
     if (lane <= N) {
       const int* l = a.st.loc + ((size_t)e * (N + 1) + lane) * 2;
@@ -201,7 +203,7 @@ __global__ void pp_step_kernel(PPArgs a, const int32_t* __restrict__ act, int ac
         d[1] = cc;
       }
     }
-    if (lane <= N) {
+    if (obs && lane <= N) {
       s_r[lane] = rr;
       s_c[lane] = cc;
     }
@@ -231,16 +233,17 @@ int pp_launch(const ic3_pp_cfg* cfg, const ic3_pp_state* st, const int32_t* act,
   const int V = cfg->dim * cfg->dim + 4;
   const int NA = ic3_pp_agents(*cfg);
   const size_t smem = obs ? (size_t)NA * W * W * sizeof(uint32_t) : 0;
-  const int threads = obs ? 256 : 32;
+  const int threads = obs ? 256 : 32 * IC3_ENV_WARPS;
+  const int grid = obs ? cfg->B : (cfg->B + IC3_ENV_WARPS - 1) / IC3_ENV_WARPS;
   const bool vec4 = (V % 4 == 0) && ((reinterpret_cast<uintptr_t>(obs) & 15) == 0);
   RolloutOpt ro = make_rollout_opt(r);
   // small observation batches stay in L2 for the encoder that follows (see IC3_OBS_L2_KEEP_BYTES)
   const int keep = obs && (size_t)cfg->B * NA * W * W * V * sizeof(float) <= IC3_OBS_L2_KEEP_BYTES;
   if (vec4)
-    IC3_LAUNCH_RC(ic3_launch_pdl(pp_step_kernel<true>, dim3(cfg->B), dim3(threads), smem, s, a, act, act_stride, reward, obs,
+    IC3_LAUNCH_RC(ic3_launch_pdl(pp_step_kernel<true>, dim3(grid), dim3(threads), smem, s, a, act, act_stride, reward, obs,
                                  err, ro, do_step, keep));
   else
-    IC3_LAUNCH_RC(ic3_launch_pdl(pp_step_kernel<false>, dim3(cfg->B), dim3(threads), smem, s, a, act, act_stride, reward, obs,
+    IC3_LAUNCH_RC(ic3_launch_pdl(pp_step_kernel<false>, dim3(grid), dim3(threads), smem, s, a, act, act_stride, reward, obs,
                                  err, ro, do_step, keep));
   return IC3_OK;
 }

@@ -95,11 +95,12 @@ __global__ void tj_step_kernel(TJArgs a, const int32_t* __restrict__ act, int ac
   extern __shared__ uint32_t s_cell[];
   __shared__ int s_r[IC3_MAX_AGENTS], s_c[IC3_MAX_AGENTS], s_alive[IC3_MAX_AGENTS], s_rid[IC3_MAX_AGENTS],
       s_lact[IC3_MAX_AGENTS];
-  const int e = blockIdx.x;
   const ic3_tj_cfg& cfg = a.cfg;
   const int N = cfg.N;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (warp == 0) {
+  // with an observation block to write: one CTA per env, warp 0 owns the state; without: one WARP per env (pp_env.cu)
+  const int e = obs ? (int)blockIdx.x : (int)(blockIdx.x * (blockDim.x >> 5)) + warp;
+  if (obs ? warp == 0 : e < cfg.B) {
     const size_t i = (size_t)e * N + lane;
     int rr = 0, cc = 0, alive = 0, wait = 0, rid = -1, rpos = -1, lact = 0;
     if (lane < N) {
@@ -229,7 +230,7 @@ __global__ void tj_step_kernel(TJArgs a, const int32_t* __restrict__ act, int ac
         if (r.io.snap_tj_route_id) r.io.snap_tj_route_id[k] = rid;
       }
     }
-    if (lane < N) {
+    if (obs && lane < N) {
       s_r[lane] = rr;
       s_c[lane] = cc;
       s_alive[lane] = alive;
@@ -263,10 +264,11 @@ int tj_launch(const ic3_tj_cfg* cfg, const ic3_tj_state* st, const int32_t* act,
   TJArgs a{*cfg, *st};
   const int W = 2 * cfg->vision + 1;
   const size_t smem = obs ? (size_t)cfg->N * W * W * sizeof(uint32_t) : 0;
-  const int threads = obs ? 128 : 32;
+  const int threads = obs ? 128 : 32 * IC3_ENV_WARPS;
+  const int grid = obs ? cfg->B : (cfg->B + IC3_ENV_WARPS - 1) / IC3_ENV_WARPS;
   RolloutOpt ro = make_rollout_opt(r);
   const int keep = obs && (size_t)cfg->B * cfg->N * (2 + W * W * cfg->vocab) * sizeof(float) <= IC3_OBS_L2_KEEP_BYTES;
-  IC3_LAUNCH_RC(ic3_launch_pdl(tj_step_kernel, dim3(cfg->B), dim3(threads), smem, s, a, act, act_stride, draws, reward, obs, err,
+  IC3_LAUNCH_RC(ic3_launch_pdl(tj_step_kernel, dim3(grid), dim3(threads), smem, s, a, act, act_stride, draws, reward, obs, err,
                                ro, do_step, keep));
   return IC3_OK;
 }
