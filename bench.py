@@ -260,6 +260,7 @@ def gpu_arm(opts):
         a = make_args(opts.workload, rank, obs_mode, nenvs)
         a.policy_impl = opts.policy_impl
         a.obs_chunk_mb = opts.obs_chunk_mb
+        a.fuse_heads = bool(int(os.environ.get("IC3_FUSE_HEADS", "0")))      # experiment: heads finished in the env step
         for k, v in extra.items():
             setattr(a, k, v)
         env = data.init(a.env_name, a)

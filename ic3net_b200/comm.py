@@ -24,7 +24,7 @@ from .lazy_obs import LazyObs
 
 def _as_u8(v, B, N, device):
     """info['comm_action'] / info['alive_mask'] (numpy or tensor, [N] or [B,N]) -> uint8 [B,N]."""
-    if torch.is_tensor(v) and v.dtype == torch.uint8 and v.dim() == 2 and v.is_contiguous():
+    if torch.is_tensor(v) and v.dtype == torch.uint8 and tuple(v.shape) == (B, N) and v.is_contiguous():
         return v if v.is_cuda else v.to(device, non_blocking=True)     # the common case: one (async if pinned) copy
     if torch.is_tensor(v) and v.is_cuda:
         t = v if v.dtype == torch.uint8 else (v != 0).to(torch.uint8)
@@ -172,6 +172,11 @@ class CommNetMLP(nn.Module):
     def _apply(self, fn, *a, **kw):
         self.__dict__['_plist'] = None
         return super(CommNetMLP, self)._apply(fn, *a, **kw)
+
+    def load_state_dict(self, *a, **kw):
+        out = super(CommNetMLP, self).load_state_dict(*a, **kw)
+        self.invalidate_packed()             # assign=True installs new Parameter objects
+        return out
 
     def packed(self):
         """K-major kernel layout of the parameters; re-packed (one kernel) when any parameter changed."""
