@@ -721,6 +721,12 @@ def gen_enemy_comm_cases():
                      dim=5, vision=1, max_steps=20, hid_size=128, ic3net=True, enemy_comm=True)
     gen_grad_case("grad_pp_enemy_ic3net_h128", 68, 5, 78, env_name="predator_prey", nagents=3, dim=5, vision=1,
                   max_steps=12, hid_size=128, ic3net=True, enemy_comm=True, batch_size=40, detach_gap=5)
+    # plain CommNet (everybody talks, the prey included), cooperative rewards, entropy bonus, normalised advantages
+    gen_episode_case("ep_pp_enemy_commnet_coop", 49, (1,), 59, hsteps=(0, 1, 6), env_name="predator_prey", nagents=4,
+                     dim=4, vision=0, max_steps=15, hid_size=128, commnet=True, enemy_comm=True, mode="cooperative")
+    gen_grad_case("grad_pp_enemy_commnet_entr_h128", 69, 2, 79, env_name="predator_prey", nagents=4, dim=4, vision=0,
+                  max_steps=10, hid_size=128, commnet=True, enemy_comm=True, mode="cooperative", batch_size=30,
+                  entr=0.01, mean_ratio=1.0, gamma=0.9, normalize_rewards=True)
 
 
 def gen_hid128_grad_cases():
