@@ -6,6 +6,7 @@ explicit 24-bit draws; ``translate_action`` keeps the reference's return shape
 ``(action, actual)`` = per-head lists, now of ``[B, N]`` int32 CUDA tensors.
 """
 import ctypes as C
+import weakref
 
 import numpy as np
 import torch
@@ -32,7 +33,7 @@ def parse_action_args(args):
         raise RuntimeError("--nactions wrong format!")
 
 
-_ticks = {}
+_ticks = {}          # id(args) -> (weak reference to args, per-env call counter [B] int32)
 _cfgs = {}          # sampler launch descriptors by (B, N, heads, env_id0, seed)
 
 
@@ -80,10 +81,14 @@ def select_action(args, action_out, draws=None, tick=None):
         d = torch.as_tensor(np.asarray(draws.cpu() if torch.is_tensor(draws) else draws, dtype=np.int64))
         d = d.to(logp.device, torch.int32).reshape(B, N, len(heads)).contiguous()
     elif tick is None:
-        key = id(args)
-        if key not in _ticks or _ticks[key].shape[0] != B:
-            _ticks[key] = torch.zeros(B, dtype=torch.int32, device=logp.device)
-        tick, bump = _ticks[key], True
+        ent = _ticks.get(id(args))
+        if ent is None or ent[0]() is not args or ent[1].shape[0] != B or ent[1].device != logp.device:
+            try:
+                ref = weakref.ref(args)          # a recycled id() of a dead namespace must not inherit its counter
+            except TypeError:
+                ref = (lambda a=args: a)
+            ent = _ticks[id(args)] = (ref, torch.zeros(B, dtype=torch.int32, device=logp.device))
+        tick, bump = ent[1], True
     action = torch.empty(B, N, len(heads), dtype=torch.int32, device=logp.device)
     _lib.check(_lib.load().ic3_sample_actions(C.byref(cfg), logp.data_ptr(), _lib.ptr(tick), _lib.ptr(d),
                                               action.data_ptr(), _lib.stream()))
