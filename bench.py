@@ -398,6 +398,10 @@ def gpu_arm(opts):
         dense_e2e = e2e_loop(a, env, net, min(max(K, 100), 200), np, torch, select_action)
         mine["dense_obs_api"] = dict(value=dense_e2e["value"], ms_per_step=dense_e2e["ms_per_step"],
                                      note="same loop with env.step returning the dense [B,N,O] tensor (per rank)")
+        try:
+            mine["trainer_run_batch"] = trainer_api_leg(opts, build, world, dev, dist, torch)
+        except Exception as ex:                               # e.g. no room for the pinned host copy of the batch
+            mine["trainer_run_batch"] = dict(unavailable=repr(ex)[:200])
         if world > 1:
             agg = torch.tensor([mine["seconds"], float(mine["steps"])], device=dev, dtype=torch.float64)
             mx = agg.clone()
@@ -566,6 +570,42 @@ def train_leg(opts, build, MultiGPUTrainer, world, dev, dist, torch):
                 replica_max_abs_diff=mgt.replica_checksum(), collectives_per_update=mgt.collectives / max(1, opts.train_updates + 1)
                 if world > 1 else 0,
                 api="MultiGPUTrainer.train_batch (all ranks; device time, max over ranks)")
+
+
+def trainer_api_leg(opts, build, world, dev, dist, torch, calls=2):
+    """The call a reference user makes for a rollout (main.py -> Trainer.run_batch, trainer.py:227-242), end to end:
+    ``batch, stat = Trainer.run_batch(epoch)`` with the reference batch boundary, then EVERY array of the returned
+    batch copied to pinned host memory (the reference hands its batch back as host data), wall clock, max over ranks.
+    Reported beside the per-step host loop (which stays the e2e headline: it crosses the PCIe bus twice per step)."""
+    a, env, net, tr = build("index", None, batch_size=opts.train_batch_size, batch_boundary=opts.train_boundary,
+                            use_graph=not opts.no_graph)
+    N = a.nagents
+    batch, stat = tr.run_batch(0)                             # warm-up: buffers, graph capture
+    host = {k: torch.empty(v.shape, dtype=v.dtype).pin_memory() for k, v in batch._asdict().items()}
+    nbytes = sum(v.numel() * v.element_size() for v in host.values())
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    steps = 0
+    t0 = time.perf_counter()
+    for k in range(calls):
+        batch, stat = tr.run_batch(k + 1)                     # includes the stat vector's device->host copy
+        for f, v in batch._asdict().items():
+            host[f].copy_(v, non_blocking=True)
+        torch.cuda.synchronize()
+        steps += int(stat["num_steps"])
+    dt = time.perf_counter() - t0
+    agg = torch.tensor([dt, float(steps)], device=dev, dtype=torch.float64)
+    if world > 1:
+        mx, sm = agg.clone(), agg.clone()
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+        dt, steps = float(mx[0].item()), float(sm[1].item())
+    T = tr.batch_plan()[0]
+    return dict(value=steps * N / dt, unit="agent-env-steps/s", calls=calls, lock_steps_per_call=T,
+                ms_per_call=1e3 * dt / calls, d2h_bytes_per_call=nbytes * world, d2h_bytes_per_step=nbytes * world // T,
+                api="Trainer.run_batch (reference batch boundary, batch_size %d) + every array of the returned batch "
+                    "copied to pinned host memory; wall clock, max over ranks" % a.batch_size)
 
 
 def per_kernel_times(tr, a, env, net, steps, C, torch, _lib):
