@@ -189,3 +189,32 @@ def test_gym_wrapper_matches_reference_properties(kind):
     env = _FakeEnv(gspaces, kind)
     a, b = GymWrapper(env), ref.GymWrapper(env)
     assert (a.observation_dim, a.num_actions, a.dim_actions) == (b.observation_dim, b.num_actions, b.dim_actions)
+
+
+def test_enemy_comm_derived_args_and_stat_split():
+    """--enemy_comm host logic (main.py:124-131; trainer.py:73-75,86-88,120-121): the prey joins the agents of the policy,
+    and its reward / gate sums are reported under their own keys.  CPU only: derive_args and the host half of
+    Trainer.stat_from_vector."""
+    from types import SimpleNamespace
+    from ic3net_b200 import main as cli
+    from ic3net_b200.trainer import Trainer
+    a = cli.derive_args(argparse.Namespace(ic3net=True, env_name="predator_prey", nagents=3, nenemies=1, enemy_comm=True,
+                                           plot=False, display=False, commnet=False, hard_attn=False, mean_ratio=1.0))
+    assert (a.nfriendly, a.nagents) == (3, 4) and a.commnet and a.hard_attn and a.mean_ratio == 0
+    with pytest.raises(RuntimeError):          # main.py:129-130
+        cli.derive_args(argparse.Namespace(ic3net=False, env_name="predator_prey", nagents=3, enemy_comm=True, plot=False,
+                                           display=False))
+    # stat vector layout: [episodes, steps, success, flags, reward[N], comm_action[N]] with N = 4 agent rows
+    v = np.array([5, 40, 2, 0, -1.0, -2.0, -3.0, 1.5, 7, 8, 9, 4], dtype=np.float64)
+    fake = SimpleNamespace(args=a, is_tj=False)
+    a.mode = "mixed"
+    st = Trainer.stat_from_vector(fake, v)
+    assert st["num_episodes"] == 5 and st["num_steps"] == 40 and st["steps_taken"] == 40 and st["success"] == 2
+    assert np.array_equal(st["reward"], [-1.0, -2.0, -3.0]) and np.array_equal(st["enemy_reward"], [1.5])
+    assert np.array_equal(st["comm_action"], [7, 8, 9]) and np.array_equal(st["enemy_comm"], [4])
+    b = argparse.Namespace(**{**vars(a), "enemy_comm": False, "nfriendly": 4})
+    st = Trainer.stat_from_vector(SimpleNamespace(args=b, is_tj=False), v)
+    assert len(st["reward"]) == 4 and "enemy_reward" not in st and "enemy_comm" not in st
+    v[3] = 0x10
+    with pytest.raises(RuntimeError):          # a device-side error flag is never swallowed
+        Trainer.stat_from_vector(fake, v)
