@@ -71,3 +71,41 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 txt = open(os.path.join(dp, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle", txt, flags=re.M), f
+
+
+def test_entry_points_validate_arguments_before_touching_the_device(built_lib):
+    """Error behaviour of the boundary: a bad call returns IC3_E_NULL / IC3_E_RANGE / IC3_E_UNSUPPORTED from the host-side
+    checks (the conditions under which the reference raises -- wrong mode predator_prey_env.py:269, too many agents -- or
+    configurations the kernels do not implement); nothing is launched, so this runs without a GPU."""
+    from ic3net_b200 import _lib
+    lib = _lib.load()
+    E_NULL, E_RANGE, E_UNSUPPORTED = -1, -2, -3
+    fake = 0x1000                      # never dereferenced: validation fails first
+    st = _lib.PPState(loc=fake, reached=fake, done=fake, success=fake, episode=fake, tick=fake)
+    ok = dict(B=4, N=3, dim=5, vision=1, mode=0, naction=5, env_id0=0, enemy_comm=0, seed=1)
+    assert lib.ic3_pp_step(None, ctypes.byref(st), fake, 1, fake, None, fake, None, None) == E_NULL
+    assert lib.ic3_pp_reset(ctypes.byref(_lib.PPCfg(**ok)), ctypes.byref(_lib.PPState()), None, None, None) == E_NULL
+    for bad in (dict(N=32), dict(N=0), dict(mode=3), dict(naction=6), dict(dim=200), dict(vision=8), dict(dim=1)):
+        cfg = _lib.PPCfg(**dict(ok, **bad))
+        assert lib.ic3_pp_step(ctypes.byref(cfg), ctypes.byref(st), fake, 1, fake, None, fake, None, None) == E_RANGE, bad
+    assert lib.ic3_pp_step(ctypes.byref(_lib.PPCfg(**ok)), ctypes.byref(st), None, 1, fake, None, fake, None,
+                           None) == E_NULL                   # no actions
+    # policy: hidden sizes / head layouts the kernels do not cover
+    hd = (ctypes.c_int32 * _lib.MAX_HEADS)(5, 2, 0, 0)
+    pol = dict(B=4, N=3, H=128, O=29, nheads=2, head_dim=hd, hard_attn=1, comm_avg=1, comm_mask_zero=0, env_id0=0, seed=1,
+               obs_off=0, obs_vocab=0, obs_ncount=0, cell=_lib.CELL_LSTM, passes=1, x_tanh=0, h_from_x=0)
+    w, io = _lib.PolicyPacked(), _lib.PolicyIO()
+    call = lambda **kw: lib.ic3_policy_step(ctypes.byref(_lib.PolicyCfg(**dict(pol, **kw))), ctypes.byref(w),
+                                            ctypes.byref(io), None)
+    assert call(H=100) == E_UNSUPPORTED and call(nheads=0) == E_RANGE and call(N=33) == E_RANGE
+    assert call(passes=_lib.MAX_PASSES + 1) == E_RANGE and call(cell=7) == E_RANGE
+    assert call() == E_NULL                                   # valid configuration, but no packed weights / buffers
+    assert lib.ic3_policy_step(None, ctypes.byref(w), ctypes.byref(io), None) == E_NULL
+    assert lib.ic3_policy_workspace_bytes(ctypes.byref(_lib.PolicyCfg(**dict(pol, H=64)))) == 0    # SIMT: no workspace
+    assert lib.ic3_policy_workspace_bytes(ctypes.byref(_lib.PolicyCfg(**pol))) > 0
+    assert lib.ic3_bptt_workspace_bytes(None) == 0
+    assert lib.ic3_sample_actions(ctypes.byref(_lib.PolicyCfg(**pol)), None, None, None, None, None) == E_NULL
+    for code, word in ((E_RANGE, b"range"), (E_UNSUPPORTED, b"not implemented"), (0, b"ok")):
+        assert word in lib.ic3_strerror(code)
+    with pytest.raises(RuntimeError, match="range"):
+        _lib.check(E_RANGE)
