@@ -69,7 +69,9 @@ def build_parser():
     parser.add_argument('--comm_init', default='uniform', type=str, help='how to initialise comm weights [uniform|zeros]')
     parser.add_argument('--hard_attn', default=False, action='store_true', help='hard attention: action - talk|silent')
     parser.add_argument('--comm_action_one', default=False, action='store_true', help='always talk')
-    parser.add_argument('--advantages_per_action', default=False, action='store_true')
+    parser.add_argument('--advantages_per_action', default=False, action='store_true',
+                        help='accepted; the per-head products of trainer.py:189-199 sum to the same loss and gradient '
+                             '(tests/test_host_logic.py pins that on the reference), so there is one code path')
     parser.add_argument('--share_weights', default=False, action='store_true', help='Share weights for hops')
     # B200 additions
     parser.add_argument('--nenvs', type=int, default=1024, help='environment slots per GPU')

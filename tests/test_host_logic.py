@@ -218,3 +218,56 @@ def test_enemy_comm_derived_args_and_stat_split():
     v[3] = 0x10
     with pytest.raises(RuntimeError):          # a device-side error flag is never swallowed
         Trainer.stat_from_vector(fake, v)
+
+
+def test_advantages_per_action_is_the_same_loss_in_the_reference():
+    """--advantages_per_action (trainer.py:189-199) multiplies the advantage into every head's log-probability before the
+    sum instead of after it: the loss -- and therefore the gradient -- is the same number.  This repo accepts the flag and
+    has one code path; the claim is pinned here on the unmodified reference (skipped where it is not present)."""
+    from oracle import ref_shims
+    if not ref_shims.reference_available():
+        pytest.skip("reference checkout not present")
+    import torch
+    from oracle.gen_golden import RefRandom, make_weights, routed
+    ref_shims.install()
+    prev = torch.get_default_dtype()
+    torch.set_default_dtype(torch.float64)
+    try:
+        from comm import CommNetMLP
+        from trainer import Trainer
+        out = []
+        for flag in (False, True):
+            a = ref_shims.make_args(env_name="predator_prey", nagents=3, dim=5, vision=1, max_steps=8, hid_size=16,
+                                    ic3net=True, batch_size=16, advantages_per_action=flag)
+            w = ref_shims.make_ref_env(a)
+            ref_shims.finish_args(a, w)
+            net = CommNetMLP(a, a.num_inputs)
+            sd = make_weights(7, a.num_inputs, a.hid_size, a.naction_heads, a.comm_init)
+            net.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()})
+            tr = Trainer(a, net, w)
+            rr = RefRandom(19, 0)
+            orig_step, orig_reset = w.step, w.reset
+
+            def step(action, _o=orig_step, _rr=rr):
+                _rr.group = -1
+                o = _o(action)
+                _rr.tick += 1
+                _rr.head = 0
+                return o
+
+            def reset(epoch, _o=orig_reset, _rr=rr):
+                o = _o(epoch)
+                _rr.episode += 1
+                return o
+            w.step, w.reset = step, reset
+            with routed(rr):
+                batch, stat = tr.run_batch(0)
+            tr.optimizer.zero_grad()
+            s = tr.compute_grad(batch)
+            out.append((s, {k: v.grad.clone() for k, v in net.named_parameters() if v.grad is not None}))
+        (s0, g0), (s1, g1) = out
+        assert np.isclose(s0["action_loss"], s1["action_loss"], rtol=1e-12, atol=1e-12)
+        for k in g0:
+            assert torch.allclose(g0[k], g1[k], rtol=1e-10, atol=1e-12), k
+    finally:
+        torch.set_default_dtype(prev)
