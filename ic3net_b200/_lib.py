@@ -89,7 +89,7 @@ class PolicyIO(C.Structure):
     _fields_ = [("x", _p), ("h", _p), ("c", _p), ("comm_action", _p), ("alive", _p), ("fresh", _p), ("tick", _p),
                 ("draws", _p), ("h_out", _p), ("c_out", _p), ("value", _p), ("logp", _p), ("action", _p),
                 ("workspace", _p), ("err", _p), ("pp_env", _p), ("pp_state", _p), ("tj_env", _p), ("tj_state", _p),
-                ("x_table", _p), ("defer_heads", C.c_int32), ("reserved0", C.c_int32)]
+                ("x_table", _p), ("defer_heads", C.c_int32), ("pass_index", C.c_int32)]
 
 
 class BpttPlan(C.Structure):

@@ -117,17 +117,18 @@ class CommNetMLP(nn.Module):
         self._plist = None
         self._packed = None
         self._packed_key = None
-        # 'tc' = tcgen05 tensor-core path (csrc/policy_tc.cu: hid_size 128, LSTM cell, one comm pass),
-        # 'simt' = fp32 CUDA-core kernel (every variant)
+        # 'tc' = tcgen05 tensor-core path (csrc/policy_tc.cu: hid_size 128, LSTM cell on the encoded observation, any
+        # number of comm passes), 'simt' = fp32 CUDA-core kernel (every variant)
+        self.tc_capable = (var['cell'] == _lib.CELL_LSTM and not var['x_tanh'] and not var['h_from_x'])
         want = getattr(args, 'policy_impl', None)
-        self.policy_impl = want or ('tc' if (H == 128 and not self.is_variant) else 'simt')
+        self.policy_impl = want or ('tc' if (H == 128 and self.tc_capable) else 'simt')
         if self.policy_impl not in ('tc', 'simt'):
             raise ValueError("policy_impl must be 'tc' or 'simt'")
         if self.policy_impl == 'tc' and H != 128:
             raise NotImplementedError("the tensor-core policy path is specialised for hid_size 128")
-        if self.policy_impl == 'tc' and self.is_variant:
-            raise NotImplementedError("the tensor-core policy path implements the recurrent LSTM policy with one comm "
-                                      "pass; this variant runs on policy_impl='simt'")
+        if self.policy_impl == 'tc' and not self.tc_capable:
+            raise NotImplementedError("the tensor-core policy path implements the recurrent LSTM policy; the tanh-cell "
+                                      "variants run on policy_impl='simt'")
         self._ws = {}
         self._xtab, self._xtab_key = None, None     # per-position encoder table of forward() on observation handles
 
@@ -198,8 +199,8 @@ class CommNetMLP(nn.Module):
                 self._bufs['f_wT'] = torch.empty(P, H, H, device=dev)
                 self._bufs['f_b'] = torch.empty(P, H, device=dev)
             if self.policy_impl == 'tc':
-                self._bufs['lstm_img'] = torch.empty(_lib.LSTM_IMG_BYTES, dtype=torch.uint8, device=dev)
-                self._bufs['bias_cat'] = torch.empty(4 * H, device=dev)
+                self._bufs['lstm_img'] = torch.empty(P * _lib.LSTM_IMG_BYTES, dtype=torch.uint8, device=dev)   # one per pass
+                self._bufs['bias_cat'] = torch.empty(P, 4 * H, device=dev)
                 self._bufs['flags'] = torch.zeros(1, dtype=torch.int32, device=dev)
             self._packed = _lib.PolicyPacked(**{k: v.data_ptr() for k, v in self._bufs.items()})
         for p in ps:

@@ -660,8 +660,9 @@ int policy_check(const ic3_policy_cfg* cfg) {
   return IC3_OK;
 }
 
-bool policy_is_variant(const ic3_policy_cfg* cfg) {
-  return cfg->cell != IC3_CELL_LSTM || cfg->passes > 1 || cfg->x_tanh || cfg->h_from_x;
+// tcgen05 path: LSTM cell on the encoded observation, any number of comm passes (policy_tc.cu loops them)
+bool policy_tc_capable(const ic3_policy_cfg* cfg) {
+  return cfg->cell == IC3_CELL_LSTM && !cfg->x_tanh && !cfg->h_from_x;
 }
 
 int packed_check(const ic3_policy_packed* w) {
@@ -726,7 +727,7 @@ extern "C" int ic3_policy_pack(const ic3_policy_cfg* cfg, const ic3_policy_param
     for (int i = 0; i < (cfg->passes > 1 ? cfg->passes : 1); ++i)
       if (!p->f_w_pass[i] || !p->f_b_pass[i]) return IC3_E_NULL;
   }
-  if (policy_is_variant(cfg) && (out->lstm_img || out->bias_cat)) return IC3_E_UNSUPPORTED;   // variants: SIMT kernel only
+  if (!policy_tc_capable(cfg) && (out->lstm_img || out->bias_cat)) return IC3_E_UNSUPPORTED;  // tanh cells: SIMT kernel only
   for (int k = 0; k < cfg->nheads; ++k)
     if (!p->head_w[k] || !p->head_b[k]) return IC3_E_NULL;
   pack_kernel<<<296, 256, 0, (cudaStream_t)stream>>>(*cfg, *p, *out);
@@ -856,7 +857,7 @@ extern "C" int ic3_policy_step(const ic3_policy_cfg* cfg, const ic3_policy_packe
   if (cfg->hard_attn && !io->comm_action) return IC3_E_NULL;
   if (cfg->N > ROWS) return IC3_E_RANGE;
   if (io->workspace && w->lstm_img) {     // tcgen05 path (policy_tc.cu); otherwise the fp32 SIMT kernel below
-    if (policy_is_variant(cfg)) return IC3_E_UNSUPPORTED;
+    if (!policy_tc_capable(cfg)) return IC3_E_UNSUPPORTED;
     return ic3_tc_policy_step(cfg, w, io, (cudaStream_t)stream);
   }
   if (!io->x) return IC3_E_NULL;

@@ -77,8 +77,10 @@ static int launch_lstm_pair(const ic3_policy_cfg* cfg, const ic3_policy_io* io, 
   la[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   la[1].val.programmaticStreamSerializationAllowed = 1;
   lc.attrs = la; lc.numAttrs = ic3_pdl_enabled() ? 2 : 1;
-  const __half* b_img = reinterpret_cast<const __half*>(w->lstm_img) + B_IMG_HALFS;   // the pair-layout copy
-  cudaError_t e = cudaLaunchKernelEx(&lc, kern, *cfg, *io, a_img, b_img, (const float*)w->bias_cat, nitems,
+  const __half* b_img = reinterpret_cast<const __half*>(w->lstm_img) + (size_t)io->pass_index * 2 * B_IMG_HALFS +
+                        B_IMG_HALFS;                                                  // the pair-layout copy
+  cudaError_t e = cudaLaunchKernelEx(&lc, kern, *cfg, *io, a_img, b_img,
+                                     (const float*)w->bias_cat + (size_t)io->pass_index * 4 * TC_H, nitems,
                                      (const float*)w->head_w, nout, partial);
   ++g_ic3_launches;
   return e == cudaSuccess ? IC3_OK : (int)e;
@@ -113,8 +115,9 @@ static int launch_lstm(const ic3_policy_cfg* cfg, const ic3_policy_io* io, const
   la[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   la[1].val.programmaticStreamSerializationAllowed = 1;
   lc.attrs = la; lc.numAttrs = ic3_pdl_enabled() ? 2 : 1;
-  const __half* b_img = reinterpret_cast<const __half*>(w->lstm_img);
-  cudaError_t e = cudaLaunchKernelEx(&lc, kern, *cfg, *io, a_img, b_img, (const float*)w->bias_cat, nitems,
+  const __half* b_img = reinterpret_cast<const __half*>(w->lstm_img) + (size_t)io->pass_index * 2 * B_IMG_HALFS;
+  cudaError_t e = cudaLaunchKernelEx(&lc, kern, *cfg, *io, a_img, b_img,
+                                     (const float*)w->bias_cat + (size_t)io->pass_index * 4 * TC_H, nitems,
                                      (const float*)w->head_w, nout, partial);
   ++g_ic3_launches;
   return e == cudaSuccess ? IC3_OK : (int)e;
@@ -136,8 +139,10 @@ uint64_t ic3_tc_workspace_bytes(const ic3_policy_cfg* cfg) {
   const long R = (long)cfg->B * cfg->N;
   const long ntiles = (R + TC_M - 1) / TC_M;
   const long ntiles_pad = (ntiles + TC_TILE_PAD - 1) / TC_TILE_PAD * TC_TILE_PAD;   // whole clusters of tiles
-  // operand image + per-slot partial logits [R][NSLOT][HEAD_PAD]
-  return (uint64_t)ntiles_pad * TC_NCHUNK * A_CHUNK_BYTES + (uint64_t)R * NSLOT * HEAD_PAD * sizeof(float);
+  // operand image + per-slot partial logits [R][NSLOT][HEAD_PAD] (+ comm_passes > 1: two (h, c) pairs that carry the
+  // state from one pass to the next)
+  const uint64_t carry = cfg->passes > 1 ? (uint64_t)4 * R * TC_H * sizeof(float) : 0;
+  return (uint64_t)ntiles_pad * TC_NCHUNK * A_CHUNK_BYTES + (uint64_t)R * NSLOT * HEAD_PAD * sizeof(float) + carry;
 }
 
 extern "C" const float* ic3_policy_partial_ptr(const ic3_policy_cfg* cfg, const void* workspace) {
@@ -159,8 +164,15 @@ int ic3_tc_pack(const ic3_policy_cfg* cfg, const ic3_policy_params* p, const ic3
     cudaError_t e = cudaMemsetAsync(out->flags, 0, sizeof(int32_t), s);
     if (e != cudaSuccess) return (int)e;
   }
-  pack_tc_kernel<<<(total + 255) / 256, 256, 0, s>>>(*p, reinterpret_cast<__half*>(out->lstm_img), out->bias_cat, out->flags);
-  IC3_LAUNCH_CHECK();
+  const int P = cfg->passes > 1 ? cfg->passes : 1;
+  for (int ps = 0; ps < P; ++ps) {           // pass i folds C_modules[i] (comm.py:63-70; share_weights: the same module)
+    ic3_policy_params q = *p;
+    if (ps > 0 && p->c_w_pass[ps]) q.c_w = p->c_w_pass[ps];
+    if (ps > 0 && p->c_b_pass[ps]) q.c_b = p->c_b_pass[ps];
+    pack_tc_kernel<<<(total + 255) / 256, 256, 0, s>>>(q, reinterpret_cast<__half*>(out->lstm_img) + (size_t)ps * 2 * B_IMG_HALFS,
+                                                       out->bias_cat + (size_t)ps * 4 * TC_H, out->flags);
+    IC3_LAUNCH_CHECK();
+  }
   return IC3_OK;
 }
 
@@ -196,9 +208,39 @@ extern "C" int ic3_policy_step_profile(const ic3_policy_cfg* cfg, const ic3_poli
   return IC3_OK;
 }
 
+static int tc_pass(const ic3_policy_cfg* cfg, const ic3_policy_packed* w, const ic3_policy_io* io, cudaStream_t s, bool last);
+
+// comm.py:179-218: `passes` rounds of (communicate, LSTM cell) on the same encoded observation.  Pass i reads the
+// state pass i-1 wrote (two carry buffers behind the workspace, alternating) and uses weight image i; only the last
+// pass writes the caller's h_out / c_out and finishes the heads.
 int ic3_tc_policy_step(const ic3_policy_cfg* cfg, const ic3_policy_packed* w, const ic3_policy_io* io, cudaStream_t s) {
   if (cfg->H != TC_H) return IC3_E_UNSUPPORTED;
   if (!io->workspace || !w->lstm_img || !w->bias_cat) return IC3_E_NULL;
+  const int P = cfg->passes > 1 ? cfg->passes : 1;
+  if (P == 1) return tc_pass(cfg, w, io, s, true);
+  const long R = (long)cfg->B * cfg->N;
+  ic3_policy_cfg c1 = *cfg;
+  c1.passes = 1;
+  float* carry = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(io->workspace) + ic3_tc_workspace_bytes(&c1));
+  const size_t RH = (size_t)R * TC_H;
+  for (int ps = 0; ps < P; ++ps) {
+    ic3_policy_io q = *io;
+    q.pass_index = ps;
+    if (ps > 0) {
+      q.h = carry + (size_t)((ps - 1) & 1) * 2 * RH;
+      q.c = q.h + RH;
+    }
+    if (ps < P - 1) {
+      q.h_out = carry + (size_t)(ps & 1) * 2 * RH;
+      q.c_out = q.h_out + RH;
+    }
+    const int rc = tc_pass(cfg, w, &q, s, ps == P - 1);
+    if (rc) return rc;
+  }
+  return IC3_OK;
+}
+
+static int tc_pass(const ic3_policy_cfg* cfg, const ic3_policy_packed* w, const ic3_policy_io* io, cudaStream_t s, bool last) {
   const long R = (long)cfg->B * cfg->N;
   const int ntiles = (int)((R + TC_M - 1) / TC_M);
   const int ntiles_pad = (ntiles + TC_TILE_PAD - 1) / TC_TILE_PAD * TC_TILE_PAD;   // padding tiles are written as zeros
@@ -271,6 +313,7 @@ int ic3_tc_policy_step(const ic3_policy_cfg* cfg, const ic3_policy_packed* w, co
   }
   if (rc) return rc;
   prof_mark(2, s);
+  if (!last) return IC3_OK;                  // heads after the last comm pass only
   if (fused_heads && io->defer_heads) {      // the env step kernel finishes the heads (ic3_rollout_io.head_partial)
     prof_mark(3, s);
     return IC3_OK;

@@ -182,8 +182,8 @@ __global__ void __launch_bounds__(256) prep_kernel(ic3_policy_cfg cfg, ic3_polic
       }
       int cm = 1;
       if (cfg.hard_attn) cm = fr ? 0 : (io.comm_action[(size_t)e * N + i] != 0);   // comm.py:171-175
-      // episode start: every agent of the env has h = 0 (trainer.py:50-51) -> nothing to send
-      g = fr ? 0.f : (float)(al * cm);
+      // episode start: every agent of the env has h = 0 (trainer.py:50-51) -> nothing to send in the first comm pass
+      g = (fr && io.pass_index == 0) ? 0.f : (float)(al * cm);
       if (cfg.comm_avg && n_alive > 1) den = (float)(n_alive - 1);                  // comm.py:194-196
     }
     s_gate[w] = g;
@@ -372,7 +372,7 @@ __global__ void __launch_bounds__(256) prep_kernel(ic3_policy_cfg cfg, ic3_polic
     float4 xv = zero4, hv = zero4, sv = zero4;
     if (row < R) {
       const int e = row / N;
-      const bool fr = io.fresh && io.fresh[e];
+      const bool fr = io.fresh && io.fresh[e] && io.pass_index == 0;     // zero state: first comm pass only
       if (XSRC == XSRC_TENSOR) {
         xv = __ldg(reinterpret_cast<const float4*>(io.x + (size_t)row * TC_H) + q);
       } else if (!TAB) {
@@ -552,7 +552,7 @@ __device__ __forceinline__ void load_cold(const ic3_policy_cfg& cfg, const ic3_p
   const int row = tile * TC_M + quarter * 32 + lane;
   const bool inrange = row < R;
   bool fr = false;
-  if (inrange && io.fresh) fr = io.fresh[row / cfg.N] != 0;
+  if (inrange && io.fresh && io.pass_index == 0) fr = io.fresh[row / cfg.N] != 0;
   const int ubase = nh * (TC_NH / 4) + cq * 16;
 #pragma unroll
   for (int cg = 0; cg < 4; ++cg) {

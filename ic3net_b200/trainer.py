@@ -124,6 +124,8 @@ class Trainer(object):
         W = 2 * e.vision + 1
         if net.policy_impl != 'tc' or not self.use_xtable or W * W > 25 or 1 + sum(self.args.naction_heads) > 8:
             return False
+        if getattr(net, 'is_variant', False):          # the BPTT kernels differentiate ONE comm pass
+            return False
         if getattr(e, 'obs_layout', (0, 0, 0))[1] == 0:
             return False
         npos = e.obs_positions

@@ -281,7 +281,9 @@ typedef struct {
    *   shared-memory images, [2 column halves][12 K-chunks][hi,lo][core-matrix layout] = 786432 bytes,
    *   followed by a second copy of the same values in the layout of the 2-SM (cta_group::2) kernel,
    *   [2 column halves][12 K-chunks][2 CTA ranks][hi,lo][core-matrix layout];
-   * bias_cat: [4H] b_ih + b_hh + W_ih.c_b, column 4*u+gate. */
+   * bias_cat: [4H] b_ih + b_hh + W_ih.c_b, column 4*u+gate.
+   * comm_passes > 1 (LSTM cell only): `passes` such image pairs / bias vectors one after the other, pass i folded
+   *   with C_modules[i] (comm.py:63-70). */
   void* lstm_img;
   float* bias_cat;
   /* variants: c_wT / c_b hold `passes` consecutive [H, H] / [H] blocks; IC3_CELL_TANH: f_wT [passes][H, H]
@@ -343,7 +345,9 @@ typedef struct {
   /* tcgen05 path with at most 7 action logits: 1 = stop after the LSTM kernel and leave the heads' partial logits in
    * the workspace (ic3_policy_partial_ptr); the env step kernel finishes them (ic3_rollout_io.head_partial). */
   int32_t defer_heads;
-  int32_t reserved0;
+  int32_t pass_index;         /* callers pass 0.  comm_passes > 1 on the tcgen05 path: the library runs the step once per
+                                 pass on a private copy of this struct and numbers the copies here (a fresh episode's
+                                 zero state applies to pass 0 only; its masks to every pass, comm.py:179-218) */
 } ic3_policy_io;
 
 /* Partial-logit block inside a tcgen05 workspace (NULL when the configuration does not use it). */

@@ -700,6 +700,10 @@ def gen_variant_cases():
                      comm_passes=2, use_alive=True)
     gen_variant_case("var_commnet_share3", 92, 45, (5,), "commnet", nagents=4, hid_size=64, commnet=True,
                      comm_passes=3, share_weights=True)
+    gen_variant_case("var_commnet_share3_h128", 98, 45, (5,), "commnet", nagents=5, hid_size=128, commnet=True,
+                     comm_passes=3, share_weights=True, comm_mode="sum")
+    gen_variant_case("var_commnet_passes4_h128", 99, 61, (2, 2), "commnet", nagents=7, hid_size=128, ic3net=True,
+                     comm_passes=4, use_alive=True)
     gen_variant_case("var_commnet_nonrec2", 93, 61, (2, 2), "commnet", nagents=6, hid_size=128, ic3net=True,
                      recurrent=False, comm_passes=2, use_alive=True)
     gen_variant_case("var_commnet_nonrec_share", 94, 29, (5,), "commnet", nagents=3, hid_size=32, commnet=True,

@@ -33,10 +33,15 @@ def build(meta, z, policy_impl=None):
     return a, net
 
 
+@pytest.mark.parametrize("impl", [None, "simt"])
 @pytest.mark.parametrize("name", golden_names("var_"))
-def test_variant_forward_matches_reference(name):
+def test_variant_forward_matches_reference(name, impl):
+    """impl None = the implementation the module picks (tcgen05 for the LSTM-cell variants at hid_size 128, whatever the
+    number of comm passes); 'simt' = the fp32 kernel forced on those same cases."""
     meta, z = load_golden(name)
-    a, net = build(meta, z)
+    a, net = build(meta, z, impl)
+    if impl == "simt" and not (net.tc_capable and a.hid_size == 128):
+        pytest.skip("the module picks the SIMT kernel for this case anyway")
     n, H = a.nagents, a.hid_size
     nrep = z["obs"].shape[0]
     B = nrep                                              # all fixture cases as ONE batch of independent envs
@@ -64,18 +69,23 @@ def test_variant_forward_matches_reference(name):
         assert close(h2.reshape(B, n, H).cpu().numpy(), z["h2"]), name
     if c2 is not None:
         assert close(c2.reshape(B, n, H).cpu().numpy(), z["c2"]), name
-    expect_tc = meta["model"] == "rnn" and meta["lstm"] and H == 128     # the LSTM baseline is the default kernel config
+    expect_tc = impl is None and bool(meta["lstm"]) and H == 128        # LSTM cell on the encoded observation
     assert (net.policy_impl == "tc") == expect_tc
+    if expect_tc:
+        net.check_errors()                                               # pipeline watchdog / fp16 range flags
 
 
-def test_variant_on_tensor_core_path_is_refused():
-    meta, z = load_golden("var_commnet_passes2")
-    with pytest.raises(NotImplementedError):
-        build(meta, z, policy_impl="tc")
+def test_tanh_cell_variant_on_tensor_core_path_is_refused():
+    for name in ("var_commnet_nonrec2", "var_mlp", "var_rnn_tanh"):
+        meta, z = load_golden(name)
+        with pytest.raises(NotImplementedError):
+            build(meta, z, policy_impl="tc")
 
 
 @pytest.mark.parametrize("model,extra", [("rnn", dict(rnn_type="MLP")), ("rnn", dict(rnn_type="LSTM")), ("mlp", {}),
                                          ("commnet", dict(comm_passes=2, share_weights=True)),
+                                         ("commnet", dict(comm_passes=3, hard_attn=False)),
+                                         ("commnet", dict(comm_passes=2, share_weights=True, policy_impl="simt")),
                                          ("commnet", dict(recurrent=False, comm_passes=2))])
 def test_variant_trains_and_recompute_agrees_with_the_kernels(model, extra):
     """A full update (rollout kernels -> compute_grad -> RMSprop) for every family, and the differentiable recompute
