@@ -733,6 +733,16 @@ def gen_enemy_comm_cases():
                   entr=0.01, mean_ratio=1.0, gamma=0.9, normalize_rewards=True)
 
 
+def gen_nostay_cases():
+    """--no_stay (predator_prey_env.py:88-92): four actions, the policy's env head has four logits."""
+    gen_env_case("env_pp_nostay", 25, 18, 2, env_name="predator_prey", nagents=3, dim=4, vision=1, no_stay=True)
+    gen_episode_case("ep_pp_nostay_commnet", 50, (0, 2), 60, hsteps=(0, 1, 5), env_name="predator_prey", nagents=3,
+                     dim=4, vision=1, max_steps=15, hid_size=128, commnet=True, no_stay=True)
+    # competitive rewards under policy-driven actions (0.05 / n_on, no 'success' statistic: :264-266, :284)
+    gen_episode_case("ep_pp_comp_ic3net", 51, (1, 4), 61, hsteps=(0, 1, 9), env_name="predator_prey", nagents=4,
+                     dim=3, vision=1, max_steps=20, hid_size=128, ic3net=True, mode="competitive")
+
+
 def gen_hid128_grad_cases():
     """Gradient fixtures at hid_size 128 (the shape the tensor-core rollout and the BPTT kernels run at) covering the
     loss / comm variants: entropy bonus, normalised advantages, cooperative returns, comm_mode sum, plain CommNet (no
@@ -753,6 +763,11 @@ def main():
         import warnings
         warnings.filterwarnings("ignore")
         gen_variant_cases()
+        return 0
+    if "--nostay-only" in sys.argv:
+        import warnings
+        warnings.filterwarnings("ignore")
+        gen_nostay_cases()
         return 0
     if "--enemy-only" in sys.argv:
         import warnings
@@ -832,6 +847,7 @@ def main():
                   batch_size=50, mean_ratio=0.5, gamma=0.9)
     gen_hid128_grad_cases()
     gen_enemy_comm_cases()
+    gen_nostay_cases()
     gen_variant_cases()
     gen_rmsprop_case("rmsprop_ref", 81)
     gen_log_case()
