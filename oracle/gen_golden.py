@@ -733,6 +733,16 @@ def gen_enemy_comm_cases():
                   entr=0.01, mean_ratio=1.0, gamma=0.9, normalize_rewards=True)
 
 
+def gen_baseline_geometry_grad_cases():
+    """Gradient fixtures at the GEOMETRY of the BASELINE configs c2 (predator-prey hard: 10 agents, dim 20, vision 1,
+    O = 3636) and c5 (traffic junction hard: 20 cars, dim 18, 56 routes) -- shorter episodes, one env."""
+    gen_grad_case("grad_pp_hard_ic3net_h128", 70, 6, 80, env_name="predator_prey", nagents=10, dim=20, vision=1,
+                  max_steps=20, hid_size=128, ic3net=True, batch_size=35, detach_gap=8)
+    gen_grad_case("grad_tj_hard_ic3net_h128", 71, 3, 81, env_name="traffic_junction", nagents=20, dim=18, vision=0,
+                  max_steps=25, hid_size=128, ic3net=True, difficulty="hard", add_rate_min=0.2, add_rate_max=0.2,
+                  batch_size=40, detach_gap=10)
+
+
 def gen_nostay_cases():
     """--no_stay (predator_prey_env.py:88-92): four actions, the policy's env head has four logits."""
     gen_env_case("env_pp_nostay", 25, 18, 2, env_name="predator_prey", nagents=3, dim=4, vision=1, no_stay=True)
@@ -763,6 +773,11 @@ def main():
         import warnings
         warnings.filterwarnings("ignore")
         gen_variant_cases()
+        return 0
+    if "--baseline-grad-only" in sys.argv:
+        import warnings
+        warnings.filterwarnings("ignore")
+        gen_baseline_geometry_grad_cases()
         return 0
     if "--nostay-only" in sys.argv:
         import warnings
@@ -848,6 +863,7 @@ def main():
     gen_hid128_grad_cases()
     gen_enemy_comm_cases()
     gen_nostay_cases()
+    gen_baseline_geometry_grad_cases()
     gen_variant_cases()
     gen_rmsprop_case("rmsprop_ref", 81)
     gen_log_case()
